@@ -1,0 +1,115 @@
+/* seacells_b200 - C ABI of the B200-native SEACells hot paths.
+ *
+ * The reference (dpeerlab/SEACells v0.3.3) has no FFI: its boundary is the Python object returned by
+ * SEACells.core.SEACells (core.py:13-100).  These entry points are what that class's methods bind when the two
+ * data-parallel hot paths move to the GPU; each one cites the reference method it replaces.  The Python mirror of the
+ * class lives in seacells_b200/core.py and reaches this library through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an SC_ERR_* code; sc_last_error() gives the message; nothing throws
+ *   - data pointers may be HOST or DEVICE addresses (detected with cudaPointerGetAttributes); results are written to
+ *     whichever kind of buffer the caller supplies; the caller owns every buffer it passes
+ *   - handles own their device scratch; work is queued on the context's stream and the call returns after the
+ *     results it promises are complete
+ *   - indices are int32, archetype/cell positions are 0-based, values are IEEE fp64
+ */
+#ifndef SEACELLS_B200_H
+#define SEACELLS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_ERR_CUDA 1
+#define SC_ERR_ARG 2
+#define SC_ERR_STATE 3
+#define SC_ERR_CAPACITY 4
+#define SC_ERR_NCCL 5
+
+typedef struct sc_ctx sc_ctx;             /* one per process / GPU */
+typedef struct sc_kernel_graph sc_kernel; /* device-resident kernel matrix M (build_graph.py:188 self.M) */
+typedef struct sc_fit sc_fit;             /* device-resident model state (cpu.py:97-111: K, A_, B_, A0, B0) */
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int sc_ctx_create(int device, sc_ctx** out);
+void sc_ctx_destroy(sc_ctx* ctx);
+const char* sc_last_error(sc_ctx* ctx);
+unsigned long long sc_launch_count(sc_ctx* ctx); /* kernels launched by this library so far */
+int sc_sync(sc_ctx* ctx);
+void* sc_stream(sc_ctx* ctx); /* cudaStream_t the library launches on (for CUDA-event timing) */
+const char* sc_version(void);
+
+/* ---- hot path 1: kernel construction  (build_graph.SEACellGraph.rbf, build_graph.py:113-189) -------------------- */
+
+/* Replaces scanpy.pp.neighbors(ad, use_rep, n_neighbors, knn=True) at build_graph.py:125 with an exact brute-force
+ * kNN over X [n x d] (float32 when x_is_f64 == 0, else float64).  Rows [row_begin,row_end) are the queries.
+ * idx_out / d2_out: [(row_end-row_begin) x (n_neighbors-1)], neighbours by (squared distance, index), self excluded. */
+int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int row_begin, int row_end,
+           int32_t* idx_out, double* d2_out);
+
+/* SEACellGraph.rbf(k, graph_construction) (build_graph.py:113): kNN, sigma (18-34), union/intersection (155-164),
+ * Gaussian values (37-61), CSR (181-188).  intersection: 0 = "union", 1 = "intersect"/"intersection". */
+int sc_kernel_build(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int intersection,
+                    sc_kernel** out, long long* nnz_out);
+/* Same, from a kNN graph the caller already holds (idx/d2 as produced by sc_knn for all n rows). */
+int sc_kernel_build_from_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors,
+                             const int32_t* idx, const double* d2, int intersection, sc_kernel** out,
+                             long long* nnz_out);
+/* Copy M out as CSR (indptr [n+1], indices/data [nnz]) plus sigma [n] and the kNN graph; any pointer may be NULL. */
+int sc_kernel_export(sc_ctx* ctx, sc_kernel* km, int32_t* indptr, int32_t* indices, double* data, double* sigma,
+                     int32_t* knn_idx, double* knn_d2);
+void sc_kernel_free(sc_kernel* km);
+
+/* Y[r x c] = S[r x m] * X[m x c], S in CSR, X and Y dense row-major fp64 (the reference's K @ B with a dense B,
+ * cpu_dense.py:353,389 / gpu.py:429,477).  Utility + roofline probe; the fit loop itself uses compressed operands. */
+int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, const int32_t* indices,
+                    const double* data, const double* X, double* Y);
+
+/* ---- hot path 2: Frank-Wolfe fit  (cpu.py:204-285, 425-536, 558-651) -------------------------------------------- */
+int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out);
+void sc_fit_destroy(sc_fit* fit);
+
+/* add_precomputed_kernel_matrix (cpu.py:115-128): M as CSR with sorted columns; K = M M^T is applied, never formed */
+int sc_fit_set_kernel(sc_fit* fit, const int32_t* indptr, const int32_t* indices, const double* data, long long nnz);
+int sc_fit_set_kernel_from(sc_fit* fit, sc_kernel* km); /* device-to-device hand-off from sc_kernel_build */
+
+/* initialize (cpu.py:237-244): B0 = one-hot at (archetypes[a], a) */
+int sc_fit_set_archetypes(sc_fit* fit, const int64_t* cell_positions /* [k], host */);
+/* initial_assignments (cpu.py:246-264): A0 as CSC (column j = cell j), already L1-column-normalised by the caller */
+int sc_fit_set_A_csc(sc_fit* fit, const int64_t* colptr /* [n+1] */, const int32_t* rows, const double* vals);
+/* restore compressed state (resume): slots are [cols x S] with S = max_FW_iter, cnt [cols] */
+int sc_fit_set_A_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt);
+int sc_fit_set_B_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt);
+
+/* _updateA (cpu.py:425-459; l2_penalty as cpu_dense.py:360).  trace: NULL or host int32 [max_FW_iter x n] that
+ * receives the argmin of every Frank-Wolfe step (test hook for argmin-sequence parity). */
+int sc_fit_update_A(sc_fit* fit, double l2_penalty, int32_t* trace);
+/* _updateB (cpu.py:461-498).  trace: NULL or host int32 [max_FW_iter x k]. */
+int sc_fit_update_B(sc_fit* fit, int32_t* trace);
+/* compute_RSS (cpu.py:520-536): || M - (M B) A ||_F via the trace identity, no n x n product */
+int sc_fit_rss(sc_fit* fit, double* rss_out);
+/* initialize + _fit (cpu.py:204-285, 595-651) for already-set archetypes and A0.  threshold_inout: <= 0 on entry
+ * means "unset" (then epsilon * RSS0 is stored, cpu.py:279-285); rss_out receives RSS_iters (RSS0 first). */
+int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsilon, double l2_penalty,
+               double* threshold_inout, int* n_iter_out, int* converged_out, double* rss_out, int rss_cap,
+               int* n_rss_out);
+
+/* compressed results: idx/val [cols x S], cnt [cols]; column j of A_ is cell j, column a of B_ is archetype a */
+int sc_fit_slots(sc_fit* fit); /* S */
+int sc_fit_get_A(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt);
+int sc_fit_get_B(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt);
+/* get_hard_assignments (cpu.py:710-722): argmax over each column of A_, first index on ties */
+int sc_fit_hard_assignments(sc_fit* fit, int32_t* labels /* [n] */);
+/* get_hard_archetypes (cpu.py:724-729): B_.argmax(0) as cell positions */
+int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells /* [k] */);
+/* get_soft_assignments (cpu_dense.py:586-605): `top` rounds of argmax with masking; idx/w [n x top] */
+int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
+/* diagnostics: [0] cells that took the generic path in the last _updateA, [1] nnz(t2) of the last _updateB */
+int sc_fit_stats(sc_fit* fit, long long* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

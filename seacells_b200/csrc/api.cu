@@ -1,0 +1,368 @@
+// extern "C" surface declared in include/seacells_b200.h
+#include <new>
+
+#include "../../include/seacells_b200.h"
+#include "common.cuh"
+#include "fit.cuh"
+#include "kernel_build.cuh"
+
+namespace {
+
+// stage a host-or-device input on the device; `own` keeps the staging buffer alive
+template <typename T>
+int to_device(sc_ctx* ctx, const T* src, size_t count, DBuf<T>& own, const T** out) {
+  if (sc_is_device_ptr(src)) {
+    *out = src;
+    return SC_OK;
+  }
+  SC_TRY(own.ensure(ctx, count ? count : 1));
+  SC_CUDA(ctx, sc_copy(own.p, src, sizeof(T) * count, ctx->stream));
+  *out = own.p;
+  return SC_OK;
+}
+
+// ---- dense-RHS CSR SpMM: one warp per (row, 256-column chunk), 8-byte lanes vectorised as double2
+__global__ void __launch_bounds__(256)
+k_spmm_csr_dense(int r, int c, const int* __restrict__ indptr, const int* __restrict__ indices,
+                 const double* __restrict__ data, const double* __restrict__ X, double* __restrict__ Y, int chunks) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)r * chunks) return;
+  const int row = (int)(w / chunks), ch = (int)(w - (long long)row * chunks);
+  const int c0 = ch * 256 + lane * 2;
+  const int s0 = indptr[row], s1 = indptr[row + 1];
+  double acc[4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+  const bool vec_ok = (c % 2 == 0);
+  for (int base = s0; base < s1; base += 32) {
+    int q = 0;
+    double m = 0.0;
+    if (base + lane < s1) {
+      q = indices[base + lane];
+      m = data[base + lane];
+    }
+    const int cnt = min(32, s1 - base);
+    for (int e = 0; e < cnt; ++e) {
+      const int qq = __shfl_sync(0xffffffffu, q, e);
+      const double mm = __shfl_sync(0xffffffffu, m, e);
+      const double* xr = X + (size_t)qq * c;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c0 + u * 64;
+        if (vec_ok && cc + 1 < c) {
+          const double2 xv = *reinterpret_cast<const double2*>(xr + cc);
+          acc[u][0] = fma(mm, xv.x, acc[u][0]);
+          acc[u][1] = fma(mm, xv.y, acc[u][1]);
+        } else {
+          if (cc < c) acc[u][0] = fma(mm, xr[cc], acc[u][0]);
+          if (cc + 1 < c) acc[u][1] = fma(mm, xr[cc + 1], acc[u][1]);
+        }
+      }
+    }
+  }
+  double* yr = Y + (size_t)row * c;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int cc = c0 + u * 64;
+    if (vec_ok && cc + 1 < c) {
+      *reinterpret_cast<double2*>(yr + cc) = make_double2(acc[u][0], acc[u][1]);
+    } else {
+      if (cc < c) yr[cc] = acc[u][0];
+      if (cc + 1 < c) yr[cc + 1] = acc[u][1];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sc_version(void) { return "seacells_b200 0.1 (sm_100a)"; }
+
+int sc_ctx_create(int device, sc_ctx** out) {
+  if (!out) return SC_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return SC_ERR_CUDA;  // no usable CUDA device: there is no CPU fallback
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return SC_ERR_CUDA;
+  sc_ctx* c = new (std::nothrow) sc_ctx();
+  if (!c) return SC_ERR_CUDA;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return SC_ERR_CUDA;
+  }
+  *out = c;
+  return SC_OK;
+}
+
+void sc_ctx_destroy(sc_ctx* ctx) {
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* sc_last_error(sc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+unsigned long long sc_launch_count(sc_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+void* sc_stream(sc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int sc_sync(sc_ctx* ctx) {
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hot path 1
+int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int row_begin, int row_end,
+           int32_t* idx_out, double* d2_out) {
+  if (!ctx || !X || !idx_out || !d2_out || n <= 0 || d <= 0) return SC_ERR_ARG;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t esz = x_is_f64 ? 8 : 4;
+  DBuf<char> xs;
+  const char* Xd = nullptr;
+  SC_TRY(to_device<char>(ctx, (const char*)X, (size_t)n * d * esz, xs, &Xd));
+  const int kk = n_neighbors - 1;
+  const size_t rows = (size_t)(row_end - row_begin);
+  const bool out_dev = sc_is_device_ptr(idx_out);
+  DBuf<int> di;
+  DBuf<double> dd;
+  int* pi = idx_out;
+  double* pd = d2_out;
+  if (!out_dev) {
+    SC_TRY(di.ensure(ctx, rows * kk + 1));
+    SC_TRY(dd.ensure(ctx, rows * kk + 1));
+    pi = di.p;
+    pd = dd.p;
+  }
+  SC_TRY(sc_knn_exact_dev(ctx, Xd, x_is_f64, n, d, n_neighbors, row_begin, row_end, pi, pd));
+  if (!out_dev) {
+    SC_CUDA(ctx, sc_copy(idx_out, pi, sizeof(int) * rows * kk, ctx->stream));
+    SC_CUDA(ctx, sc_copy(d2_out, pd, sizeof(double) * rows * kk, ctx->stream));
+  }
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors,
+                             const int32_t* idx, const double* d2, int intersection, sc_kernel** out,
+                             long long* nnz_out) {
+  if (!ctx || !X || !out || n <= 0 || d <= 0) return SC_ERR_ARG;
+  if (intersection != 0 && intersection != 1) SC_FAIL(ctx, SC_ERR_ARG, "graph_construction must be union or intersection");
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  *out = nullptr;
+  const size_t esz = x_is_f64 ? 8 : 4;
+  DBuf<char> xs;
+  const char* Xd = nullptr;
+  SC_TRY(to_device<char>(ctx, (const char*)X, (size_t)n * d * esz, xs, &Xd));
+  sc_kernel_graph* km = new (std::nothrow) sc_kernel_graph();
+  if (!km) SC_FAIL(ctx, SC_ERR_CUDA, "out of host memory");
+  const int kk = n_neighbors - 1;
+  km->kk = kk;
+  int rc = km->knn_idx.ensure(ctx, (size_t)n * kk + 1);
+  if (rc == SC_OK) rc = km->knn_d2.ensure(ctx, (size_t)n * kk + 1);
+  if (rc == SC_OK) {
+    if (idx && d2) {
+      if (cudaMemcpyAsync(km->knn_idx.p, idx, sizeof(int) * (size_t)n * kk, cudaMemcpyDefault, ctx->stream) != cudaSuccess ||
+          cudaMemcpyAsync(km->knn_d2.p, d2, sizeof(double) * (size_t)n * kk, cudaMemcpyDefault, ctx->stream) != cudaSuccess) {
+        ctx->err = "kernel_build: copying the kNN graph failed";
+        rc = SC_ERR_CUDA;
+      }
+    } else {
+      rc = sc_knn_exact_dev(ctx, Xd, x_is_f64, n, d, n_neighbors, 0, n, km->knn_idx.p, km->knn_d2.p);
+    }
+  }
+  if (rc == SC_OK) rc = km->build(ctx, Xd, x_is_f64, n, d, n_neighbors, km->knn_idx.p, km->knn_d2.p, intersection);
+  if (rc != SC_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    delete km;
+    return rc;
+  }
+  if (nnz_out) *nnz_out = km->nnz;
+  *out = km;
+  return SC_OK;
+}
+
+int sc_kernel_build(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int intersection,
+                    sc_kernel** out, long long* nnz_out) {
+  return kernel_build_impl(ctx, X, x_is_f64, n, d, n_neighbors, nullptr, nullptr, intersection, out, nnz_out);
+}
+
+int sc_kernel_build_from_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors,
+                             const int32_t* idx, const double* d2, int intersection, sc_kernel** out,
+                             long long* nnz_out) {
+  if (!idx || !d2) return SC_ERR_ARG;
+  return kernel_build_impl(ctx, X, x_is_f64, n, d, n_neighbors, idx, d2, intersection, out, nnz_out);
+}
+
+int sc_kernel_export(sc_ctx* ctx, sc_kernel* km, int32_t* indptr, int32_t* indices, double* data, double* sigma,
+                     int32_t* knn_idx, double* knn_d2) {
+  if (!ctx || !km) return SC_ERR_ARG;
+  const size_t n = km->n, nnz = km->nnz, kk = km->kk;
+  if (indptr) SC_CUDA(ctx, sc_copy(indptr, km->indptr.p, sizeof(int) * (n + 1), ctx->stream));
+  if (indices) SC_CUDA(ctx, sc_copy(indices, km->indices.p, sizeof(int) * nnz, ctx->stream));
+  if (data) SC_CUDA(ctx, sc_copy(data, km->data.p, sizeof(double) * nnz, ctx->stream));
+  if (sigma) SC_CUDA(ctx, sc_copy(sigma, km->sigma.p, sizeof(double) * n, ctx->stream));
+  if (knn_idx) SC_CUDA(ctx, sc_copy(knn_idx, km->knn_idx.p, sizeof(int) * n * kk, ctx->stream));
+  if (knn_d2) SC_CUDA(ctx, sc_copy(knn_d2, km->knn_d2.p, sizeof(double) * n * kk, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+void sc_kernel_free(sc_kernel* km) { delete km; }
+
+int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, const int32_t* indices,
+                    const double* data, const double* X, double* Y) {
+  if (!ctx || r <= 0 || m <= 0 || c <= 0 || !indptr || !indices || !data || !X || !Y) return SC_ERR_ARG;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int h_nnz = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, indptr + r, sizeof(int), cudaMemcpyDefault, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DBuf<int> sp, sc;
+  DBuf<double> sv, sx, sy;
+  const int *dp, *dc;
+  const double *dv, *dx;
+  SC_TRY(to_device<int>(ctx, indptr, (size_t)r + 1, sp, &dp));
+  SC_TRY(to_device<int>(ctx, indices, (size_t)h_nnz, sc, &dc));
+  SC_TRY(to_device<double>(ctx, data, (size_t)h_nnz, sv, &dv));
+  SC_TRY(to_device<double>(ctx, X, (size_t)m * c, sx, &dx));
+  const bool y_dev = sc_is_device_ptr(Y);
+  double* dy = Y;
+  if (!y_dev) {
+    SC_TRY(sy.ensure(ctx, (size_t)r * c));
+    dy = sy.p;
+  }
+  const int chunks = (c + 255) / 256;
+  const long long warps = (long long)r * chunks;
+  SC_LAUNCH(ctx, k_spmm_csr_dense, (unsigned)((warps * 32 + 255) / 256), 256, 0, r, c, dp, dc, dv, dx, dy, chunks);
+  if (!y_dev) SC_CUDA(ctx, sc_copy(Y, dy, sizeof(double) * (size_t)r * c, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hot path 2
+int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out) {
+  if (!ctx || !out) return SC_ERR_ARG;
+  *out = nullptr;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  sc_fit* f = new (std::nothrow) sc_fit();
+  if (!f) SC_FAIL(ctx, SC_ERR_CUDA, "out of host memory");
+  int rc = f->init(ctx, n_cells, n_archetypes, max_FW_iter);
+  if (rc != SC_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    delete f;
+    return rc;
+  }
+  *out = f;
+  return SC_OK;
+}
+
+void sc_fit_destroy(sc_fit* fit) {
+  if (!fit) return;
+  cudaStreamSynchronize(fit->ctx->stream);
+  delete fit;
+}
+
+int sc_fit_set_kernel(sc_fit* fit, const int32_t* indptr, const int32_t* indices, const double* data, long long nnz) {
+  if (!fit || !indptr || !indices || !data || nnz <= 0) return SC_ERR_ARG;
+  return fit->set_kernel(indptr, indices, data, nnz);
+}
+
+int sc_fit_set_kernel_from(sc_fit* fit, sc_kernel* km) {
+  if (!fit || !km) return SC_ERR_ARG;
+  if (km->n != fit->n) SC_FAIL(fit->ctx, SC_ERR_ARG, "kernel matrix dimension does not match n_cells");
+  return fit->set_kernel(km->indptr.p, km->indices.p, km->data.p, km->nnz);
+}
+
+int sc_fit_set_archetypes(sc_fit* fit, const int64_t* cell_positions) {
+  if (!fit || !cell_positions) return SC_ERR_ARG;
+  return fit->set_B_onehot((const long long*)cell_positions);
+}
+
+int sc_fit_set_A_csc(sc_fit* fit, const int64_t* colptr, const int32_t* rows, const double* vals) {
+  if (!fit || !colptr || !rows || !vals) return SC_ERR_ARG;
+  return fit->set_A_lists((const long long*)colptr, rows, vals);
+}
+
+int sc_fit_set_A_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt) {
+  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  return fit->set_A_slots(idx, val, cnt);
+}
+
+int sc_fit_set_B_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt) {
+  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  return fit->set_B_slots(idx, val, cnt);
+}
+
+static int with_trace(sc_fit* fit, int32_t* trace, size_t count, int (*fn)(sc_fit*, int*, double), double arg) {
+  sc_ctx* ctx = fit->ctx;
+  DBuf<int> td;
+  int* tp = nullptr;
+  if (trace) {
+    SC_TRY(td.ensure(ctx, count));
+    SC_CUDA(ctx, cudaMemsetAsync(td.p, 0xff, sizeof(int) * count, ctx->stream));
+    tp = td.p;
+  }
+  SC_TRY(fn(fit, tp, arg));
+  if (trace) SC_CUDA(ctx, sc_copy(trace, tp, sizeof(int) * count, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+int sc_fit_update_A(sc_fit* fit, double l2_penalty, int32_t* trace) {
+  if (!fit) return SC_ERR_ARG;
+  return with_trace(fit, trace, (size_t)fit->T * fit->n,
+                    [](sc_fit* f, int* t, double l2) { return f->update_A(l2, t); }, l2_penalty);
+}
+
+int sc_fit_update_B(sc_fit* fit, int32_t* trace) {
+  if (!fit) return SC_ERR_ARG;
+  return with_trace(fit, trace, (size_t)fit->T * fit->k, [](sc_fit* f, int* t, double) { return f->update_B(t); }, 0.0);
+}
+
+int sc_fit_rss(sc_fit* fit, double* rss_out) {
+  if (!fit || !rss_out) return SC_ERR_ARG;
+  return fit->rss(rss_out);
+}
+
+int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsilon, double l2_penalty,
+               double* threshold_inout, int* n_iter_out, int* converged_out, double* rss_out, int rss_cap,
+               int* n_rss_out) {
+  if (!fit || !threshold_inout || !n_iter_out || !converged_out || !rss_out || !n_rss_out) return SC_ERR_ARG;
+  if (max_iter < min_iter) SC_FAIL(fit->ctx, SC_ERR_ARG, "max_iter < min_iter");
+  return fit->run(max_iter, min_iter, convergence_epsilon, l2_penalty, threshold_inout, n_iter_out, converged_out,
+                  rss_out, rss_cap, n_rss_out);
+}
+
+int sc_fit_slots(sc_fit* fit) { return fit ? fit->S : 0; }
+int sc_fit_get_A(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt) {
+  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  return fit->get_A(idx, val, cnt);
+}
+int sc_fit_get_B(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt) {
+  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  return fit->get_B(idx, val, cnt);
+}
+int sc_fit_hard_assignments(sc_fit* fit, int32_t* labels) {
+  if (!fit || !labels) return SC_ERR_ARG;
+  return fit->hard_assignments(labels);
+}
+int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells) {
+  if (!fit || !cells) return SC_ERR_ARG;
+  return fit->hard_archetypes(cells);
+}
+int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w) {
+  if (!fit || !idx || !w) return SC_ERR_ARG;
+  return fit->soft_assignments(top, idx, w);
+}
+int sc_fit_stats(sc_fit* fit, long long* out2) {
+  if (!fit || !out2) return SC_ERR_ARG;
+  out2[0] = fit->last_slow_cells;
+  out2[1] = fit->last_t2_nnz;
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "spgemm_rows.cuh"
+
+// State of one SEACells model on one GPU.  See fit.cu for the layout.
+struct sc_fit {
+  sc_ctx* ctx = nullptr;
+  int n = 0, k = 0, T = 50, S = 50;
+  int hash_cap = 512;
+  // kernel matrix M
+  DBuf<int> m_ptr, m_col;
+  DBuf<double> m_val;
+  long long m_nnz = 0;
+  double m_fro2 = 0.0;
+  bool have_M = false, have_A = false, have_B = false, a_is_slots = false, pre_valid = false;
+  // compressed A (double buffered) and the initial-assignment lists
+  DBuf<int> a_idx[2], a_cnt[2];
+  DBuf<double> a_val[2];
+  int a_cur = -1;
+  DBuf<long long> slot_ptr_n;
+  RowListsBuf a0;
+  // compressed B
+  DBuf<int> b_idx, b_cnt;
+  DBuf<double> b_val;
+  // B by cell, M*B, K*B
+  RowListsBuf brow, Y, KB;
+  DBuf<double> t1A, t1B;
+  // _updateB precompute
+  RowListsBuf MA, T2c;
+  DBuf<long long> c_ptr, a_off, arow_ptr;
+  DBuf<int> c_cell;
+  DBuf<double> c_t2;
+  DBuf<unsigned long long> gk_in, gk_out;
+  DBuf<double> gv_in, gv_out;
+  // scratch
+  DBuf<int> cnt_n, cnt_k, cursor_n, slow_list, slow_cnt;
+  DBuf<double> percell, scalars;
+  SpgemmScratch sp;
+  DBuf<char> tmp;
+  // diagnostics
+  int last_slow_cells = 0;
+  long long last_t2_nnz = 0;
+
+  int init(sc_ctx* c, int n_, int k_, int T_);
+  int set_kernel(const int* indptr, const int* indices, const double* data, long long nnz);
+  int set_B_onehot(const long long* archetypes_host);
+  int set_B_slots(const int* idx, const double* val, const int* cnt);
+  int set_A_lists(const long long* colptr, const int* idx, const double* val);
+  int set_A_slots(const int* idx, const double* val, const int* cnt);
+  RowLists A_view() const;
+  int compute_KB();
+  int precompute_A();
+  int update_A(double l2, int* trace_dev);
+  int update_B(int* trace_dev);
+  int rss(double* out_host);
+  int run(int max_iter, int min_iter, double eps, double l2, double* threshold_inout, int* n_iter_out,
+          int* converged_out, double* rss_out, int rss_cap, int* n_rss_out);
+  int get_A(int* idx, double* val, int* cnt);
+  int get_B(int* idx, double* val, int* cnt);
+  int hard_assignments(int* labels);
+  int hard_archetypes(int* cells);
+  int soft_assignments(int top, int* idx, double* w);
+};

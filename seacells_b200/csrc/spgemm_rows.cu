@@ -1,0 +1,235 @@
+// Z = S * X  for a CSR matrix S (n x m, the kernel matrix M) and per-row sparse lists X (m rows keyed by archetype).
+//
+// This is the engine's "SpMM for K*B" (cpu.py:441, 481, 484 compute K@B, K@A.T with K = M M^T): two passes of this
+// kernel apply M twice, and the right-hand side stays in its compressed form, so the output never becomes the dense
+// n x k matrix the reference's gpu.py forms (107 GB at n = 1M, k = 13333).
+//
+// One warp per output row.  The row's (key, value) pairs are accumulated in a shared-memory open-addressing table.
+// Accumulation order is fixed (ascending position in the row of S, then position in the row of X): colliding
+// contributions inside one 32-wide batch are applied rank by rank, so results are bitwise reproducible.
+// Output rows are sorted by key.
+#include "common.cuh"
+#include "spgemm_rows.cuh"
+
+__global__ void k_spgemm_ub(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
+                            const int* __restrict__ x_len, long long* __restrict__ ub, int nrows_total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nrows_total) return;
+  long long u = 0;
+  if (i >= row_begin && i < row_end) {
+    for (int p = s_ptr[i]; p < s_ptr[i + 1]; ++p) u += x_len[s_col[p]];
+  }
+  ub[i] = u;  // ub[nrows_total] = 0 so that the exclusive scan ends with the total
+}
+
+__device__ __forceinline__ unsigned hash_key(int k) { return (unsigned)k * 2654435761u; }
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
+              const double* __restrict__ s_val, RowLists X, const long long* __restrict__ z_ptr,
+              int* __restrict__ z_len, int* __restrict__ z_key, double* __restrict__ z_val, int* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* tvals = reinterpret_cast<double*>(smem_raw) + (size_t)warp * CAP;
+  int* tkeys = reinterpret_cast<int*>(smem_raw + (size_t)WARPS * CAP * sizeof(double)) + (size_t)warp * CAP;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int i = row_begin + blockIdx.x * WARPS + warp; i < row_end; i += gridDim.x * WARPS) {
+    const long long zp = z_ptr[i];
+    const long long ub = z_ptr[i + 1] - zp;
+    if (ub == 0) {
+      if (lane == 0) z_len[i] = 0;
+      continue;
+    }
+    // effective table size: power of two >= 2*ub, capped at CAP
+    int cap = 64;
+    while (cap < CAP && (long long)cap < 2 * ub) cap <<= 1;
+    const int capm = cap - 1;
+    const int limit = cap - (cap >> 3);  // refuse to fill beyond 7/8
+    for (int t = lane; t < cap; t += 32) {
+      tkeys[t] = -1;
+      tvals[t] = 0.0;
+    }
+    __syncwarp();
+    int uniq = 0;
+    bool overflow = false;
+    const int s0 = s_ptr[i], s1 = s_ptr[i + 1];
+    for (int base = s0; base < s1 && !overflow; base += 32) {
+      int q = -1, xl = 0;
+      double m = 0.0;
+      long long xp = 0;
+      if (base + lane < s1) {
+        q = s_col[base + lane];
+        m = s_val[base + lane];
+        xl = X.len[q];
+        xp = X.ptr[q];
+      }
+      int incl = xl;  // inclusive warp scan of list lengths
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int tot = __shfl_sync(FULL, incl, 31);
+      for (int f0 = 0; f0 < tot; f0 += 32) {
+        const int f = f0 + lane;
+        const bool valid = f < tot;
+        // owner lane: smallest o with incl[o] > f
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          int pv = __shfl_sync(FULL, incl, lo + step - 1);
+          if (pv <= f) lo += step;
+        }
+        lo = min(lo, 31);
+        const int o_incl = __shfl_sync(FULL, incl, lo);
+        const int o_len = __shfl_sync(FULL, xl, lo);
+        const long long o_ptr = __shfl_sync(FULL, xp, lo);
+        const double o_m = __shfl_sync(FULL, m, lo);
+        int key = 0, slot = -1 - lane;
+        double c = 0.0;
+        bool is_new = false;
+        if (valid) {
+          const long long e = o_ptr + (f - (o_incl - o_len));
+          key = X.key[e];
+          c = __dmul_rn(o_m, X.val[e]);
+          int s = hash_key(key) & capm;
+          while (true) {
+            int prev = atomicCAS(&tkeys[s], -1, key);
+            if (prev == -1) {
+              is_new = true;
+              break;
+            }
+            if (prev == key) break;
+            s = (s + 1) & capm;
+          }
+          slot = s;
+        }
+        uniq += __popc(__ballot_sync(FULL, is_new));
+        if (uniq > limit) {
+          overflow = true;
+          break;
+        }
+        __syncwarp();
+        const unsigned grp = __match_any_sync(FULL, slot);
+        const int rank = __popc(grp & lt_mask);
+        const int maxcnt = __reduce_max_sync(FULL, __popc(grp));
+        for (int r = 0; r < maxcnt; ++r) {
+          if (valid && rank == r) tvals[slot] = __dadd_rn(tvals[slot], c);
+          __syncwarp();
+        }
+      }
+    }
+    if (overflow) {
+      if (lane == 0) {
+        atomicExch(&flags[0], 1);
+        z_len[i] = 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    // in-place compaction of occupied slots to [0, uniq)
+    int w = 0;
+    for (int base = 0; base < cap; base += 32) {
+      const int kk = tkeys[base + lane];
+      const double vv = tvals[base + lane];
+      const bool occ = kk != -1;
+      const unsigned ball = __ballot_sync(FULL, occ);
+      __syncwarp();
+      if (occ) {
+        const int pos = w + __popc(ball & lt_mask);
+        tkeys[pos] = kk;
+        tvals[pos] = vv;
+      }
+      w += __popc(ball);
+      __syncwarp();
+    }
+    // bitonic sort by key over the next power of two
+    int P = 1;
+    while (P < uniq) P <<= 1;
+    for (int t = uniq + lane; t < P; t += 32) tkeys[t] = 0x7fffffff;
+    __syncwarp();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < P; t += 32) {
+          const int x = t ^ j;
+          if (x > t) {
+            const int ka = tkeys[t], kb = tkeys[x];
+            const bool asc = (t & k2) == 0;
+            if ((ka > kb) == asc) {
+              tkeys[t] = kb;
+              tkeys[x] = ka;
+              const double va = tvals[t];
+              tvals[t] = tvals[x];
+              tvals[x] = va;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) z_len[i] = uniq;
+    for (int t = lane; t < uniq; t += 32) {
+      z_key[zp + t] = tkeys[t];
+      z_val[zp + t] = tvals[t];
+    }
+    __syncwarp();
+  }
+}
+
+template <int CAP, int WARPS>
+static int launch_fill(sc_ctx* ctx, int row_begin, int row_end, const CsrView& S, const RowLists& X, RowListsBuf& Z,
+                       int* flags) {
+  const size_t smem = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int rows = row_end - row_begin;
+  if (rows <= 0) return SC_OK;
+  int grid = (rows + WARPS - 1) / WARPS;
+  const int maxgrid = 148 * 16;
+  if (grid > maxgrid) grid = maxgrid;
+  SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
+            X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, flags);
+  return SC_OK;
+}
+
+int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, RowListsBuf& Z,
+                   SpgemmScratch& sc, int hash_cap) {
+  const int n = S.n;
+  SC_TRY(sc.ub.ensure(ctx, (size_t)n + 1));
+  SC_TRY(Z.ptr.ensure(ctx, (size_t)n + 1));
+  SC_TRY(Z.len.ensure(ctx, (size_t)n));
+  SC_TRY(sc.flags.ensure(ctx, 4));
+  Z.rows = n;
+  SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+  SC_LAUNCH(ctx, k_spgemm_ub, (n + 1 + 255) / 256, 256, 0, row_begin, row_end, S.indptr, S.indices, X.len, sc.ub.p, n);
+  SC_TRY(sc_exclusive_scan_i64(ctx, sc.ub.p, Z.ptr.p, (size_t)n + 1, sc.tmp));
+  long long total = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&total, Z.ptr.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  SC_TRY(Z.key.ensure(ctx, (size_t)total + 1));
+  SC_TRY(Z.val.ensure(ctx, (size_t)total + 1));
+  while (true) {
+    SC_CUDA(ctx, cudaMemsetAsync(sc.flags.p, 0, sizeof(int) * 4, ctx->stream));
+    if (hash_cap <= 512) {
+      SC_TRY((launch_fill<512, 8>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
+    } else if (hash_cap <= 4096) {
+      SC_TRY((launch_fill<4096, 2>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
+    } else {
+      SC_TRY((launch_fill<16384, 1>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
+    }
+    int flag = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&flag, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!flag) break;
+    if (hash_cap <= 512) hash_cap = 4096;
+    else if (hash_cap <= 4096) hash_cap = 16384;
+    else SC_FAIL(ctx, SC_ERR_CAPACITY, "spgemm_rows: a row has more than 14336 distinct archetypes");
+  }
+  return SC_OK;
+}

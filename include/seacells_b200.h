@@ -106,8 +106,14 @@ int sc_fit_hard_assignments(sc_fit* fit, int32_t* labels /* [n] */);
 int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells /* [k] */);
 /* get_soft_assignments (cpu_dense.py:586-605): `top` rounds of argmax with masking; idx/w [n x top] */
 int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
-/* diagnostics: [0] cells that took the generic path in the last _updateA, [1] nnz(t2) of the last _updateB */
-int sc_fit_stats(sc_fit* fit, long long* out2);
+/* diagnostics: [0] cells that took the generic path in the last _updateA, [1] nnz(t2) of the last _updateB,
+ * [2] hub archetypes (rows of A longer than 8192 cells) in the last _updateB, [3] rows of the last K*B product that
+ * needed the dense-accumulator kernel */
+int sc_fit_stats(sc_fit* fit, long long* out4);
+/* with SC_PROFILE=1 in the environment: accumulated wall seconds per stage (synchronising; development aid).
+ * [0] B-by-cell [1] M*B [2] M*(M*B) [3] t1=B^T K B [4] _updateA shared-memory path [5] _updateA generic path
+ * [6] A A^T [7] K A^T rows [8] candidates by archetype [9] _updateB gradient+argmin+step [10] RSS */
+int sc_fit_profile(sc_fit* fit, double* out16);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sc_fit_hard_archetypes": (_i, [_vp, _vp]),
     "sc_fit_soft_assignments": (_i, [_vp, _i, _vp, _vp]),
     "sc_fit_stats": (_i, [_vp, _vp]),
+    "sc_fit_profile": (_i, [_vp, _vp]),
 }
 
 

@@ -267,9 +267,18 @@ class FitEngine:
         return idx, w
 
     def stats(self):
-        out = np.zeros(2, np.int64)
+        out = np.zeros(4, np.int64)
         self.ctx.check(self.ctx.lib.sc_fit_stats(self.h, ptr(out)), "sc_fit_stats")
-        return {"slow_cells_last_update_A": int(out[0]), "t2_nnz_last_update_B": int(out[1])}
+        return {"slow_cells_last_update_A": int(out[0]), "t2_nnz_last_update_B": int(out[1]),
+                "hub_archetypes_last_update_B": int(out[2]), "dense_rows_last_spgemm": int(out[3])}
+
+    STAGES = ["brow", "M*B", "M*(M*B)", "t1A", "updA_smem", "updA_generic", "gram", "KAt_rows", "cand_by_arch",
+              "updB_step", "rss"]
+
+    def profile(self):
+        out = np.zeros(16, np.float64)
+        self.ctx.check(self.ctx.lib.sc_fit_profile(self.h, ptr(out)), "sc_fit_profile")
+        return dict(zip(self.STAGES, out.tolist()))
 
     def close(self):
         if getattr(self, "h", None) is not None:

@@ -358,10 +358,17 @@ int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w) {
   if (!fit || !idx || !w) return SC_ERR_ARG;
   return fit->soft_assignments(top, idx, w);
 }
-int sc_fit_stats(sc_fit* fit, long long* out2) {
-  if (!fit || !out2) return SC_ERR_ARG;
-  out2[0] = fit->last_slow_cells;
-  out2[1] = fit->last_t2_nnz;
+int sc_fit_stats(sc_fit* fit, long long* out4) {
+  if (!fit || !out4) return SC_ERR_ARG;
+  out4[0] = fit->last_slow_cells;
+  out4[1] = fit->last_t2_nnz;
+  out4[2] = fit->last_hubs;
+  out4[3] = fit->sp.last_big_rows;
+  return SC_OK;
+}
+int sc_fit_profile(sc_fit* fit, double* out16) {
+  if (!fit || !out16) return SC_ERR_ARG;
+  for (int i = 0; i < 16; ++i) out16[i] = fit->prof[i];
   return SC_OK;
 }
 

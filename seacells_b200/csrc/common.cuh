@@ -81,7 +81,7 @@ struct DBuf {
       p = nullptr;
       cap = 0;
     }
-    size_t want = n + n / 8 + 64;
+    size_t want = n + n / 2 + 64;  // generous slack: list sizes creep up during the Frank-Wolfe loop
     SC_CUDA(ctx, cudaMalloc((void**)&p, want * sizeof(T)));
     cap = want;
     return SC_OK;
@@ -134,6 +134,8 @@ int sc_exclusive_scan_i64(sc_ctx* ctx, const long long* in, long long* out, size
 int sc_exclusive_scan_i32_to_i64(sc_ctx* ctx, const int* in, long long* out, size_t n, DBuf<char>& tmp);
 int sc_sort_pairs_u64_f64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, double* vals_in,
                           double* vals_out, size_t n, int end_bit, DBuf<char>& tmp);
+int sc_sort_pairs_u64_u32(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, unsigned* vals_in,
+                          unsigned* vals_out, size_t n, int end_bit, DBuf<char>& tmp);
 int sc_sort_keys_u64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, size_t n, int end_bit,
                      DBuf<char>& tmp);
 int sc_sum_f64(sc_ctx* ctx, const double* in, double* out, size_t n, DBuf<char>& tmp);

@@ -32,43 +32,40 @@ __global__ void k_square(const double* __restrict__ in, double* __restrict__ out
   if (i < n) out[i] = in[i] * in[i];
 }
 
-// B by cell: count, fill, sort
-__global__ void k_brow_count(int k, int S, const int* __restrict__ b_idx, const int* __restrict__ b_cnt, int* cnt) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= k * S) return;
-  int a = e / S, s = e - a * S;
-  if (s < b_cnt[a]) atomicAdd(&cnt[b_idx[e]], 1);
-}
-__global__ void k_brow_fill(int k, int S, const int* __restrict__ b_idx, const double* __restrict__ b_val,
-                            const int* __restrict__ b_cnt, const long long* __restrict__ ptr, int* cursor, int* key,
-                            double* val) {
+// B by cell: (cell, archetype) pairs -> radix sort -> row bounds.  Rows come out sorted by archetype.
+__global__ void k_emit_b_pairs(int k, int S, const int* __restrict__ b_idx, const double* __restrict__ b_val,
+                               const int* __restrict__ b_cnt, const long long* __restrict__ off,
+                               unsigned long long* __restrict__ keys, double* __restrict__ vals) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= k * S) return;
   int a = e / S, s = e - a * S;
   if (s >= b_cnt[a]) return;
-  int cell = b_idx[e];
-  int pos = atomicAdd(&cursor[cell], 1);
-  key[ptr[cell] + pos] = a;
-  val[ptr[cell] + pos] = b_val[e];
+  keys[off[a] + s] = ((unsigned long long)(unsigned)b_idx[e] << 32) | (unsigned)a;
+  vals[off[a] + s] = b_val[e];
 }
-__global__ void k_rows_sort_small(int rows, const long long* __restrict__ ptr, const int* __restrict__ len, int* key,
-                                  double* val) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  int L = len[r];
-  if (L < 2) return;
-  long long p = ptr[r];
-  for (int i = 1; i < L; ++i) {
-    int kk = key[p + i];
-    double vv = val[p + i];
-    int j = i - 1;
-    while (j >= 0 && key[p + j] > kk) {
-      key[p + j + 1] = key[p + j];
-      val[p + j + 1] = val[p + j];
-      --j;
+__global__ void k_lists_from_sorted(int rows, long long total, const unsigned long long* __restrict__ keys,
+                                    long long* __restrict__ ptr, int* __restrict__ len, int* __restrict__ key_out) {
+  // one thread per row: ptr[r] = lower_bound(r << 32); plus unpack of the low word for the first `total` entries
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) key_out[t] = (int)(keys[t] & 0xffffffffu);
+  if (t > rows) return;
+  const unsigned long long target = (unsigned long long)(unsigned)t << 32;
+  long long lo = 0, hi = total;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1;
+    else hi = mid;
+  }
+  ptr[t] = lo;
+  if (t < rows) {
+    const unsigned long long t2 = (unsigned long long)(unsigned)(t + 1) << 32;
+    long long lo2 = lo, hi2 = total;
+    while (lo2 < hi2) {
+      long long mid = (lo2 + hi2) >> 1;
+      if (keys[mid] < t2) lo2 = mid + 1;
+      else hi2 = mid;
     }
-    key[p + j + 1] = kk;
-    val[p + j + 1] = vv;
+    len[t] = (int)(lo2 - lo);
   }
 }
 
@@ -107,129 +104,6 @@ struct UpdAArgs {
   int* slow_cnt;
 };
 
-__global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr size_t PER_WARP = (size_t)(2 * FWA_NC + FWA_TCAP) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
-  unsigned char* base = smem_raw + (size_t)warp * PER_WARP;
-  double* ct2 = reinterpret_cast<double*>(base);
-  double* ca = ct2 + FWA_NC;
-  double* Tc = ca + FWA_NC;
-  int* ck = reinterpret_cast<int*>(Tc + FWA_TCAP);
-  int* slv = ck + FWA_NC;
-  const int k = g.k, S = g.S, T = g.T;
-  const double* __restrict__ t1T = g.t1T;
-
-  for (int j = g.cell_begin + blockIdx.x * FWA_WARPS + warp; j < g.cell_end; j += gridDim.x * FWA_WARPS) {
-    const int nc = g.KB.len[j];
-    bool slow = (nc == 0 || nc > FWA_NC);
-    if (!slow) {
-      const long long kp = g.KB.ptr[j];
-      for (int c = lane; c < nc; c += 32) {
-        ck[c] = g.KB.key[kp + c];
-        ct2[c] = g.KB.val[kp + c];
-        ca[c] = 0.0;
-      }
-      __syncwarp();
-      const int scap = min(FWA_TCAP / nc, FW_SMAX);
-      // ---- t = 0: gradient against the previous A (cpu.py:447 with A = A_prev)
-      const int m0 = g.Aprev.len[j];
-      const long long pp = g.Aprev.ptr[j];
-      double bv = FW_INF;
-      int bi = 0x7fffffff;
-      for (int c = lane; c < nc; c += 32) {
-        double acc = 0.0;
-        const int id = ck[c];
-        for (int e = 0; e < m0; ++e) acc = fma(t1T[(size_t)g.Aprev.key[pp + e] * k + id], g.Aprev.val[pp + e], acc);
-        const double G = 2.0 * (acc - ct2[c]);
-        if (G < bv) {
-          bv = G;
-          bi = c;
-        }
-      }
-      warp_argmin(bv, bi);
-      if (!(bv < 0.0)) {
-        slow = true;
-      } else {
-        int cstar = bi;
-        // previous weight of the chosen archetype (A_prev[amin, j])
-        double aprev = 0.0;
-        for (int e0 = 0; e0 < m0; e0 += 32) {
-          const int e = e0 + lane;
-          const bool hit = e < m0 && g.Aprev.key[pp + e] == ck[cstar];
-          const unsigned ball = __ballot_sync(0xffffffffu, hit);
-          if (ball) {
-            const int src = __ffs(ball) - 1;
-            aprev = __shfl_sync(0xffffffffu, hit ? g.Aprev.val[pp + e] : 0.0, src);
-            break;
-          }
-        }
-        int nslots = 1;
-        if (lane == 0) {
-          slv[0] = cstar;
-          ca[cstar] = fw_step(aprev, 1.0, fw_gamma(0));
-          if (g.trace) g.trace[j] = ck[cstar];
-        }
-        if (scap > 0)
-          for (int c = lane; c < nc; c += 32) Tc[c] = t1T[(size_t)ck[cstar] * k + ck[c]];
-        __syncwarp();
-        // ---- t >= 1
-        for (int t = 1; t < T; ++t) {
-          bv = FW_INF;
-          bi = 0x7fffffff;
-          for (int c = lane; c < nc; c += 32) {
-            double acc = 0.0;
-            const int id = ck[c];
-            for (int s = 0; s < nslots; ++s) {
-              const int v = slv[s];
-              const double tv = (s < scap) ? Tc[s * nc + c] : t1T[(size_t)ck[v] * k + id];
-              acc = fma(tv, ca[v], acc);
-            }
-            const double G = 2.0 * (acc - ct2[c]);
-            if (G < bv) {
-              bv = G;
-              bi = c;
-            }
-          }
-          warp_argmin(bv, bi);
-          if (!(bv < 0.0)) {
-            slow = true;
-            break;
-          }
-          cstar = bi;
-          const double gamma = fw_gamma(t);
-          const bool was_active = ca[cstar] != 0.0;
-          __syncwarp();
-          for (int s = lane; s < nslots; s += 32) {
-            const int v = slv[s];
-            ca[v] = fw_step(ca[v], v == cstar ? 1.0 : 0.0, gamma);
-          }
-          if (!was_active) {
-            if (lane == 0) {
-              ca[cstar] = fw_step(0.0, 1.0, gamma);
-              slv[nslots] = cstar;
-            }
-            if (nslots < scap)
-              for (int c = lane; c < nc; c += 32) Tc[nslots * nc + c] = t1T[(size_t)ck[cstar] * k + ck[c]];
-            nslots++;
-          }
-          if (lane == 0 && g.trace) g.trace[(size_t)t * g.n + j] = ck[cstar];
-          __syncwarp();
-        }
-        if (!slow) {
-          for (int s = lane; s < nslots; s += 32) {
-            g.a_idx[(size_t)j * S + s] = ck[slv[s]];
-            g.a_val[(size_t)j * S + s] = ca[slv[s]];
-          }
-          if (lane == 0) g.a_cnt[j] = nslots;
-        }
-      }
-    }
-    if (slow && lane == 0) g.slow_list[atomicAdd(g.slow_cnt, 1)] = j;
-    __syncwarp();
-  }
-}
-
 // binary search for `key` in a sorted list; returns value or 0
 __device__ __forceinline__ double list_lookup(const int* __restrict__ keys, const double* __restrict__ vals, int L,
                                               int key) {
@@ -240,6 +114,153 @@ __device__ __forceinline__ double list_lookup(const int* __restrict__ keys, cons
     else hi = mid;
   }
   return (lo < L && keys[lo] == key) ? vals[lo] : 0.0;
+}
+
+constexpr size_t FWA_PER_WARP =
+    (size_t)(FWA_NC + FWA_TCAP + FW_SMAX) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
+
+// Dense-column rule when no candidate is negative: scan archetypes 0,1,2,... and stop at the first exact zero of
+// G[i] = 2 (sum_s t1[i, act_s] a_s - t2[i]); if the column has no zero, return the first minimum.
+__device__ __forceinline__ int fwA_zero_scan(int k, const double* __restrict__ t1T, const int* act_id,
+                                             const double* act_val, int nact, const int* ck, const double* ct2,
+                                             int nc, int lane) {
+  double sv = FW_INF;
+  int si = 0x7fffffff;
+  for (int i0 = 0; i0 < k; i0 += 32) {
+    const int i = i0 + lane;
+    double G = FW_INF;
+    if (i < k) {
+      double acc = 0.0;
+      for (int e = 0; e < nact; ++e) acc = fma(t1T[(size_t)act_id[e] * k + i], act_val[e], acc);
+      G = 2.0 * (acc - list_lookup(ck, ct2, nc, i));
+    }
+    const unsigned z = __ballot_sync(0xffffffffu, G == 0.0);
+    if (z) return i0 + __ffs(z) - 1;
+    if (G < sv) {  // ascending scan: strict '<' keeps the first index
+      sv = G;
+      si = i;
+    }
+  }
+  warp_argmin(sv, si);
+  return si;
+}
+
+// Shared-memory path of _updateA: one warp per cell, candidates (support of t2[:, j]) and the t1 columns of the
+// active archetypes cached in shared memory.  Handles every cell with <= FWA_NC candidates when l2_penalty == 0,
+// including cells whose gradient has no negative entry (zero scan above; the chosen archetype then lies outside the
+// candidate set and simply becomes one more active slot).
+__global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* base = smem_raw + (size_t)warp * FWA_PER_WARP;
+  double* ct2 = reinterpret_cast<double*>(base);
+  double* Tc = ct2 + FWA_NC;
+  double* sa = Tc + FWA_TCAP;
+  int* ck = reinterpret_cast<int*>(sa + FW_SMAX);
+  int* sid = ck + FWA_NC;
+  const int k = g.k, S = g.S, T = g.T;
+  const double* __restrict__ t1T = g.t1T;
+
+  for (int j = g.cell_begin + blockIdx.x * FWA_WARPS + warp; j < g.cell_end; j += gridDim.x * FWA_WARPS) {
+    const int nc = g.KB.len[j];
+    if (nc > FWA_NC) {
+      if (lane == 0) g.slow_list[atomicAdd(g.slow_cnt, 1)] = j;
+      continue;
+    }
+    const long long kp = g.KB.ptr[j];
+    for (int c = lane; c < nc; c += 32) {
+      ck[c] = g.KB.key[kp + c];
+      ct2[c] = g.KB.val[kp + c];
+    }
+    __syncwarp();
+    const int scap = nc > 0 ? min(FWA_TCAP / nc, FW_SMAX) : 0;
+    // ---- t = 0: gradient against the previous A (cpu.py:447 with A = A_prev)
+    const int m0 = g.Aprev.len[j];
+    const int* pkey = g.Aprev.key + g.Aprev.ptr[j];
+    const double* pval = g.Aprev.val + g.Aprev.ptr[j];
+    double bv = FW_INF;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < nc; c += 32) {
+      double acc = 0.0;
+      const int id = ck[c];
+      for (int e = 0; e < m0; ++e) acc = fma(t1T[(size_t)pkey[e] * k + id], pval[e], acc);
+      const double G = 2.0 * (acc - ct2[c]);
+      if (G < bv) {
+        bv = G;
+        bi = c;
+      }
+    }
+    warp_argmin(bv, bi);
+    int chosen = (bv < 0.0) ? ck[bi] : fwA_zero_scan(k, t1T, pkey, pval, m0, ck, ct2, nc, lane);
+    double aprev = 0.0;  // A_prev[chosen, j]
+    for (int e0 = 0; e0 < m0; e0 += 32) {
+      const int e = e0 + lane;
+      const bool hit = e < m0 && pkey[e] == chosen;
+      const unsigned ball = __ballot_sync(0xffffffffu, hit);
+      if (ball) {
+        aprev = __shfl_sync(0xffffffffu, hit ? pval[e] : 0.0, __ffs(ball) - 1);
+        break;
+      }
+    }
+    int nslots = 1;
+    if (lane == 0) {
+      sid[0] = chosen;
+      sa[0] = fw_step(aprev, 1.0, fw_gamma(0));  // every other entry becomes a + (0 - a) = 0 and is dropped
+      if (g.trace) g.trace[j] = chosen;
+    }
+    if (scap > 0)
+      for (int c = lane; c < nc; c += 32) Tc[c] = t1T[(size_t)chosen * k + ck[c]];
+    __syncwarp();
+    // ---- t >= 1
+    for (int t = 1; t < T; ++t) {
+      bv = FW_INF;
+      bi = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {
+        double acc = 0.0;
+        const int id = ck[c];
+        for (int s = 0; s < nslots; ++s) {
+          const double tv = (s < scap) ? Tc[s * nc + c] : t1T[(size_t)sid[s] * k + id];
+          acc = fma(tv, sa[s], acc);
+        }
+        const double G = 2.0 * (acc - ct2[c]);
+        if (G < bv) {
+          bv = G;
+          bi = c;
+        }
+      }
+      warp_argmin(bv, bi);
+      chosen = (bv < 0.0) ? ck[bi] : fwA_zero_scan(k, t1T, sid, sa, nslots, ck, ct2, nc, lane);
+      const double gamma = fw_gamma(t);
+      int pos = -1;
+      for (int s0 = 0; s0 < nslots; s0 += 32) {
+        const int s = s0 + lane;
+        const unsigned ball = __ballot_sync(0xffffffffu, s < nslots && sid[s] == chosen);
+        if (ball) {
+          pos = s0 + __ffs(ball) - 1;
+          break;
+        }
+      }
+      __syncwarp();
+      for (int s = lane; s < nslots; s += 32) sa[s] = fw_step(sa[s], s == pos ? 1.0 : 0.0, gamma);
+      if (pos < 0) {
+        if (lane == 0) {
+          sid[nslots] = chosen;
+          sa[nslots] = fw_step(0.0, 1.0, gamma);
+        }
+        if (nslots < scap)
+          for (int c = lane; c < nc; c += 32) Tc[nslots * nc + c] = t1T[(size_t)chosen * k + ck[c]];
+        nslots++;
+      }
+      if (lane == 0 && g.trace) g.trace[(size_t)t * g.n + j] = chosen;
+      __syncwarp();
+    }
+    for (int s = lane; s < nslots; s += 32) {
+      g.a_idx[(size_t)j * S + s] = sid[s];
+      g.a_val[(size_t)j * S + s] = sa[s];
+    }
+    if (lane == 0) g.a_cnt[j] = nslots;
+    __syncwarp();
+  }
 }
 
 // Generic path: exact dense-column semantics for any cell (no candidates, all-non-negative gradient, l2 > 0, ...).
@@ -396,12 +417,16 @@ __global__ void k_row_bounds(int k, const unsigned long long* __restrict__ keys,
   }
   rptr[a] = lo;
 }
-// t1B[l][a] = sum_j A[l,j] A[a,j], cells j ascending (the order of scipy's csr_matmat for A @ A.T, cpu.py:480)
-__global__ void k_gram(int k, int S, const long long* __restrict__ rptr, const unsigned long long* __restrict__ keys,
-                       const double* __restrict__ vals, const int* __restrict__ a_idx,
-                       const double* __restrict__ a_val, const int* __restrict__ a_cnt, double* __restrict__ t1) {
+// t1B[l][a] = sum_j A[l,j] A[a,j], cells j ascending (the order of scipy's csr_matmat for A @ A.T, cpu.py:480).
+// Rows longer than `hub_thr` cells ("hub" archetypes: low-index archetypes that collect a little weight from almost
+// every cell through the argmin-of-zeros rule) are skipped here and filled by k_gram_mirror / k_gram_hubpair.
+__global__ void k_gram(int k, int S, long long hub_thr, const long long* __restrict__ rptr,
+                       const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
+                       const int* __restrict__ a_idx, const double* __restrict__ a_val,
+                       const int* __restrict__ a_cnt, double* __restrict__ t1) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= k) return;
+  if (rptr[warp + 1] - rptr[warp] > hub_thr) return;
   double* row = t1 + (size_t)warp * k;
   for (long long e = rptr[warp]; e < rptr[warp + 1]; ++e) {
     const int j = (int)(keys[e] & 0xffffffffu);
@@ -414,27 +439,77 @@ __global__ void k_gram(int k, int S, const long long* __restrict__ rptr, const u
     __syncwarp();
   }
 }
+// hub row h, ordinary column a: the product terms and their order are those of t1B[a][h], so copy it
+__global__ void k_gram_mirror(int k, int nhub, const int* __restrict__ hubs, const unsigned char* __restrict__ is_hub,
+                              double* __restrict__ t1) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = hubs[blockIdx.y];
+  if (a >= k || is_hub[a]) return;
+  t1[(size_t)h * k + a] = t1[(size_t)a * k + h];
+}
+// hub x hub entries: fixed-shape parallel reduction over the cells of the first hub's row
+__global__ void __launch_bounds__(256)
+k_gram_hubpair(int k, int S, int nhub, const int* __restrict__ hubs, const long long* __restrict__ rptr,
+               const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
+               const int* __restrict__ a_idx, const double* __restrict__ a_val, const int* __restrict__ a_cnt,
+               double* __restrict__ t1) {
+  __shared__ double sh[256];
+  // blockIdx.x enumerates pairs (p, q) with p <= q
+  int p = 0, rem = blockIdx.x;
+  while (rem >= nhub - p) {
+    rem -= nhub - p;
+    p++;
+  }
+  const int q = p + rem;
+  const int l = hubs[p], l2 = hubs[q];
+  double acc = 0.0;
+  for (long long e = rptr[l] + threadIdx.x; e < rptr[l + 1]; e += 256) {
+    const int j = (int)(keys[e] & 0xffffffffu);
+    const int cnt = a_cnt[j];
+    for (int s = 0; s < cnt; ++s)
+      if (a_idx[(size_t)j * S + s] == l2) {
+        acc = __dadd_rn(acc, __dmul_rn(vals[e], a_val[(size_t)j * S + s]));
+        break;
+      }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + st]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    t1[(size_t)l * k + l2] = sh[0];
+    t1[(size_t)l2 * k + l] = sh[0];
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ candidates by archetype
-__global__ void k_count_keys(int rows, RowLists L, int* cnt) {
+// Per-cell rows of t2 = K A^T  ->  per-archetype candidate lists ordered by decreasing t2 (32-bit quantised).
+// key = archetype << 32 | ~(upper word of t2's bit pattern): t2 > 0, so the upper word is monotone in t2.
+__global__ void k_emit_cand(int rows, RowLists L, const long long* __restrict__ off,
+                            unsigned long long* __restrict__ keys, unsigned* __restrict__ pos_val,
+                            int* __restrict__ cellv, double* __restrict__ t2v) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const long long p = L.ptr[warp];
-  const int len = L.len[warp];
-  for (int x = lane; x < len; x += 32) atomicAdd(&cnt[L.key[p + x]], 1);
-}
-__global__ void k_scatter_by_key(int rows, RowLists L, const long long* __restrict__ cptr, int* cursor, int* c_cell,
-                                 double* c_val) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const long long p = L.ptr[warp];
+  const long long p = L.ptr[warp], o = off[warp];
   const int len = L.len[warp];
   for (int x = lane; x < len; x += 32) {
-    const int a = L.key[p + x];
-    const long long pos = cptr[a] + atomicAdd(&cursor[a], 1);
-    c_cell[pos] = warp;
-    c_val[pos] = L.val[p + x];
+    const double v = L.val[p + x];
+    const unsigned hi = (unsigned)((unsigned long long)__double_as_longlong(v) >> 32);
+    keys[o + x] = ((unsigned long long)(unsigned)L.key[p + x] << 32) | (unsigned)(~hi);
+    pos_val[o + x] = (unsigned)(o + x);
+    cellv[o + x] = warp;
+    t2v[o + x] = v;
   }
+}
+__global__ void k_gather_cand(long long total, const unsigned* __restrict__ order, const int* __restrict__ cellv,
+                              const double* __restrict__ t2v, int* __restrict__ c_cell, double* __restrict__ c_t2) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const unsigned src = order[e];
+  c_cell[e] = cellv[src];
+  c_t2[e] = t2v[src];
 }
 
 // ------------------------------------------------------------------------------------------------ _updateB, one FW step
@@ -452,73 +527,228 @@ struct UpdBArgs {
   int* trace;  // [T * k] or null
 };
 
-__global__ void __launch_bounds__(256) k_updateB_iter(UpdBArgs g) {
+constexpr int UPB_CHUNK = 1024;  // candidates per CTA
+
+__global__ void k_chunk_count(int k, const long long* __restrict__ c_ptr, int* __restrict__ nch) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > k) return;
+  nch[a] = (a < k) ? (int)((c_ptr[a + 1] - c_ptr[a] + UPB_CHUNK - 1) / UPB_CHUNK) : 0;
+}
+__global__ void k_chunk_fill(int k, const long long* __restrict__ chunk_ptr, int* __restrict__ chunk_arch) {
+  const int a = blockIdx.x;
+  for (long long c = chunk_ptr[a] + threadIdx.x; c < chunk_ptr[a + 1]; c += blockDim.x) chunk_arch[c] = a;
+}
+
+// block-wide lexicographic (value, index) minimum; result valid on every thread
+__device__ __forceinline__ void block_argmin_256(double& v, int& i, double* sg, int* si) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warp_argmin(v, i);
+  __syncthreads();
+  if (lane == 0) {
+    sg[warp] = v;
+    si[warp] = i;
+  }
+  __syncthreads();
+  v = sg[0];
+  i = si[0];
+  for (int w = 1; w < 8; ++w)
+    if (sg[w] < v || (sg[w] == v && si[w] < i)) {
+      v = sg[w];
+      i = si[w];
+    }
+}
+
+// largest entry of every K B row: (value, archetype); feeds the second pruning bound of k_updateB_eval
+__global__ void k_row_max(int rows, RowLists L, double* __restrict__ mv, int* __restrict__ ml) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const long long p = L.ptr[warp];
+  const int len = L.len[warp];
+  double bv = -1.0;
+  int bk = 0;
+  for (int x = lane; x < len; x += 32) {
+    const double v = L.val[p + x];
+    if (v > bv) {
+      bv = v;
+      bk = L.key[p + x];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, d);
+    if (ov > bv || (ov == bv && ok < bk)) {
+      bv = ov;
+      bk = ok;
+    }
+  }
+  if (lane == 0) {
+    mv[warp] = bv > 0.0 ? bv : 0.0;
+    ml[warp] = bk;
+  }
+}
+
+// Gradient of _updateB on the support of t2 (cpu.py:486): G[i,a] = 2 ((K B t1)[i,a] - t2[i,a]).
+// One chunk of one archetype's candidate list per CTA, one candidate per thread (rows of K B longer than UPB_LONG are
+// done by the whole warp afterwards).  Candidates are ordered by decreasing t2.  K, B, t1 >= 0 and monotone rounding
+// give two exact lower bounds on the computed G[i,a]:
+//     G >= -2 t2[i,a]                                   (the product term is >= 0)
+//     G >= 2 (fl(KBmax_i * t1[lmax_i, a]) - t2[i,a])    (a sum of non-negative terms is >= any one of them)
+// so once a first pass over the 256 largest-t2 candidates has produced a minimum `bound`, any candidate whose lower
+// bound exceeds it can neither be the argmin nor tie with it and is skipped without reading its K B row.  This is what
+// keeps "hub" archetypes (every cell is a candidate) affordable.  round 0 = first 256 candidates of every archetype,
+// round 1 = everything else.
+constexpr int UPB_LONG = 192;
+__global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, const long long* __restrict__ chunk_ptr,
+                                                      const int* __restrict__ chunk_arch,
+                                                      const double* __restrict__ cmax_v, const int* __restrict__ cmax_l,
+                                                      double* __restrict__ part_v, int* __restrict__ part_i,
+                                                      double* __restrict__ bound_v) {
   __shared__ double sg[8];
   __shared__ int si[8];
-  __shared__ double s_bestv;
-  __shared__ int s_besti;
+  int a, chunk;
+  if (round == 0) {
+    a = blockIdx.x;
+    chunk = 0;
+    if (chunk_ptr[a + 1] == chunk_ptr[a]) return;
+  } else {
+    a = chunk_arch[blockIdx.x];
+    chunk = (int)((long long)blockIdx.x - chunk_ptr[a]);
+  }
+  const int lane = threadIdx.x & 31;
+  const double* __restrict__ row = g.t1 + (size_t)a * g.k;
+  const long long c0 = g.c_ptr[a] + (long long)chunk * UPB_CHUNK;
+  const int nc = (int)min((long long)UPB_CHUNK, g.c_ptr[a + 1] - c0);
+  const double bound = (round == 0) ? FW_INF : bound_v[a];
+  const int e_begin = (round == 1 && chunk == 0) ? 256 : 0;
+  const int e_end = (round == 0) ? min(nc, 256) : nc;
+  double bv = FW_INF;
+  int bi = 0x7fffffff;
+  for (int e0 = e_begin; e0 < e_end; e0 += 256) {
+    const int e = e0 + threadIdx.x;
+    int cell = 0, L = 0;
+    long long p = 0;
+    double t2v = 0.0;
+    bool live = false;
+    if (e < e_end) {
+      t2v = g.c_t2[c0 + e];
+      const double cut = fmin(bound, bv);
+      live = !(-2.0 * t2v > cut);
+      if (live) {
+        cell = g.c_cell[c0 + e];
+        if (round == 1) {
+          const double hb = __dmul_rn(cmax_v[cell], row[cmax_l[cell]]);
+          live = !(2.0 * (hb - t2v) > cut);
+        }
+        if (live) {
+          p = g.KB.ptr[cell];
+          L = g.KB.len[cell];
+        }
+      }
+    }
+    if (live && L <= UPB_LONG) {
+      double acc = 0.0;
+      const int* __restrict__ kk = g.KB.key + p;
+      const double* __restrict__ vv = g.KB.val + p;
+#pragma unroll 4
+      for (int x = 0; x < L; ++x) acc = fma(__ldg(vv + x), __ldg(row + __ldg(kk + x)), acc);
+      const double G = 2.0 * (acc - t2v);
+      if (G < bv || (G == bv && cell < bi)) {
+        bv = G;
+        bi = cell;
+      }
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, live && L > UPB_LONG);
+    while (longmask) {
+      const int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const long long pc = __shfl_sync(0xffffffffu, p, src);
+      const int Lc = __shfl_sync(0xffffffffu, L, src);
+      double acc = 0.0;
+      for (int x = lane; x < Lc; x += 32) acc = fma(g.KB.val[pc + x], row[g.KB.key[pc + x]], acc);
+      const double H = warp_sum(acc);
+      if (lane == src) {
+        const double G = 2.0 * (H - t2v);
+        if (G < bv || (G == bv && cell < bi)) {
+          bv = G;
+          bi = cell;
+        }
+      }
+    }
+  }
+  block_argmin_256(bv, bi, sg, si);
+  if (threadIdx.x == 0) {
+    if (round == 0) {
+      bound_v[a] = bv;
+      bound_v[g.k + a] = __longlong_as_double((long long)bi);  // carried to the step kernel as the round-0 winner
+    } else {
+      part_v[chunk_ptr[a] + chunk] = bv;
+      part_i[chunk_ptr[a] + chunk] = bi;
+    }
+  }
+}
+
+// Per archetype: reduce the chunk minima, apply the dense-column rule when nothing is negative, take the simplex step.
+__global__ void __launch_bounds__(256) k_updateB_step(UpdBArgs g, const long long* __restrict__ chunk_ptr,
+                                                      const double* __restrict__ part_v,
+                                                      const int* __restrict__ part_i,
+                                                      const double* __restrict__ bound_v) {
+  __shared__ double sg[8];
+  __shared__ int si[8];
   __shared__ int s_zero;
   const int a = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = g.k, S = g.S;
   const double* __restrict__ row = g.t1 + (size_t)a * k;
-  const long long c0 = g.c_ptr[a];
-  const int nc = (int)(g.c_ptr[a + 1] - c0);
-
   double bv = FW_INF;
   int bi = 0x7fffffff;
-  for (int e = warp; e < nc; e += 8) {
-    const int cell = g.c_cell[c0 + e];
-    const double t2v = g.c_t2[c0 + e];
-    const long long p = g.KB.ptr[cell];
-    const int L = g.KB.len[cell];
-    double acc = 0.0;
-    for (int x = lane; x < L; x += 32) acc = fma(g.KB.val[p + x], row[g.KB.key[p + x]], acc);
-    const double H = warp_sum(acc);
-    const double G = 2.0 * (H - t2v);
-    if (G < bv || (G == bv && cell < bi)) {
-      bv = G;
-      bi = cell;
+  if (threadIdx.x == 0 && chunk_ptr[a + 1] > chunk_ptr[a]) {  // winner of the first 256 candidates (round 0)
+    bv = bound_v[a];
+    bi = (int)__double_as_longlong(bound_v[k + a]);
+  }
+  for (long long c = chunk_ptr[a] + threadIdx.x; c < chunk_ptr[a + 1]; c += 256) {
+    const double v = part_v[c];
+    const int i = part_i[c];
+    if (v < bv || (v == bv && i < bi)) {
+      bv = v;
+      bi = i;
     }
   }
-  if (lane == 0) {
-    sg[warp] = bv;
-    si[warp] = bi;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = sg[0];
-    int i = si[0];
-    for (int w = 1; w < 8; ++w)
-      if (sg[w] < v || (sg[w] == v && si[w] < i)) {
-        v = sg[w];
-        i = si[w];
-      }
-    s_bestv = v;
-    s_besti = i;
-    s_zero = 0x7fffffff;
-  }
-  __syncthreads();
-  int amin = s_besti;
-  if (!(s_bestv < 0.0)) {
-    // dense column scan from cell 0 with early exit at the first exact zero
-    double tv = FW_INF;
-    int ti = 0x7fffffff;
+  if (threadIdx.x == 0) s_zero = 0x7fffffff;
+  block_argmin_256(bv, bi, sg, si);
+  int amin = bi;
+  const long long ncand = g.c_ptr[a + 1] - g.c_ptr[a];
+  if (!(bv < 0.0) && ncand < (long long)g.n) {
+    // No candidate is negative, so the column minimum is >= 0 and np.argmin returns the first exact zero if there is
+    // one.  Cells outside the support of t2 have G = 2 (K B t1)[i,a] >= 0: scan them in ascending order, stop at the
+    // first zero (or once past a candidate that is itself exactly zero); candidates were already evaluated above.
+    double tv = bv;
+    int ti = bi;
     bool found = false;
-    for (int i0 = 0; i0 < g.n; i0 += 256) {
+    const int stop_at = (bv == 0.0) ? bi : g.n;
+    for (int i0 = 0; i0 < stop_at; i0 += 256) {
       const int i = i0 + threadIdx.x;
-      double G = FW_INF;
-      if (i < g.n) {
-        const long long p = g.KB.ptr[i];
-        const int L = g.KB.len[i];
-        double acc = 0.0;
-        for (int x = 0; x < L; ++x) acc = fma(g.KB.val[p + x], row[g.KB.key[p + x]], acc);
-        const double t2v = list_lookup(g.T2c.key + g.T2c.ptr[i], g.T2c.val + g.T2c.ptr[i], g.T2c.len[i], a);
-        G = 2.0 * (acc - t2v);
-        if (G == 0.0) atomicMin(&s_zero, i);
-        else if (G < tv) {
-          tv = G;
-          ti = i;
+      if (i < stop_at) {
+        const long long tp = g.T2c.ptr[i];
+        const int tl = g.T2c.len[i];
+        int lo = 0, hi = tl;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (g.T2c.key[tp + mid] < a) lo = mid + 1;
+          else hi = mid;
+        }
+        const bool is_cand = lo < tl && g.T2c.key[tp + lo] == a;
+        if (!is_cand) {
+          const long long p = g.KB.ptr[i];
+          const int L = g.KB.len[i];
+          double acc = 0.0;
+          for (int x = 0; x < L; ++x) acc = fma(g.KB.val[p + x], row[g.KB.key[p + x]], acc);
+          const double G = 2.0 * acc;
+          if (G == 0.0) atomicMin(&s_zero, i);
+          else if (G < tv || (G == tv && i < ti)) {
+            tv = G;
+            ti = i;
+          }
         }
       }
       __syncthreads();
@@ -526,31 +756,13 @@ __global__ void __launch_bounds__(256) k_updateB_iter(UpdBArgs g) {
       __syncthreads();  // everyone has read s_zero before the next chunk may lower it
       if (z != 0x7fffffff) {
         found = true;
+        amin = z;
         break;
       }
     }
-    if (found) {
-      amin = s_zero;
-    } else {
-      // block-wide lexicographic minimum
-      warp_argmin(tv, ti);
-      if (lane == 0) {
-        sg[warp] = tv;
-        si[warp] = ti;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double v = sg[0];
-        int i = si[0];
-        for (int w = 1; w < 8; ++w)
-          if (sg[w] < v || (sg[w] == v && si[w] < i)) {
-            v = sg[w];
-            i = si[w];
-          }
-        s_besti = i;
-      }
-      __syncthreads();
-      amin = s_besti;
+    if (!found) {
+      block_argmin_256(tv, ti, sg, si);
+      amin = ti;
     }
   }
   // simplex step on column a of B (cpu.py:494)
@@ -682,18 +894,34 @@ __global__ void k_soft_top(int n, int k, int S, int top, const int* __restrict__
 }
 
 // ================================================================================================ host side
+#include <chrono>
+#include <cstdlib>
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+enum { P_BROW = 0, P_SPGEMM_Y, P_SPGEMM_KB, P_T1A, P_UPDA_FAST, P_UPDA_SLOW, P_GRAM, P_T2ROWS, P_T2TRANS, P_GEVAL, P_RSS };
+void sc_fit::pstart() {
+  if (!profile) return;
+  cudaStreamSynchronize(ctx->stream);
+  prof_t0 = now_s();
+}
+void sc_fit::pstop(int stage) {
+  if (!profile) return;
+  cudaStreamSynchronize(ctx->stream);
+  prof[stage] += now_s() - prof_t0;
+}
 static int set_smem_attr_once(sc_ctx* ctx) {
   static bool done = false;
   if (done) return SC_OK;
-  constexpr size_t PER_WARP = (size_t)(2 * FWA_NC + FWA_TCAP) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
   SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(PER_WARP * FWA_WARPS)));
+                                    (int)(FWA_PER_WARP * FWA_WARPS)));
   done = true;
   return SC_OK;
 }
 
 int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
+  profile = std::getenv("SC_PROFILE") != nullptr;
   n = n_;
   k = k_;
   T = T_;
@@ -718,7 +946,6 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   SC_TRY(slow_cnt.ensure(ctx, 4));
   SC_TRY(cnt_n.ensure(ctx, (size_t)n + 1));
   SC_TRY(cnt_k.ensure(ctx, (size_t)k + 1));
-  SC_TRY(cursor_n.ensure(ctx, (size_t)n + 1));
   SC_TRY(set_smem_attr_once(ctx));
   return SC_OK;
 }
@@ -810,20 +1037,37 @@ RowLists sc_fit::A_view() const {
 int sc_fit::compute_KB() {
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   // B by cell
-  SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
-  SC_CUDA(ctx, cudaMemsetAsync(cursor_n.p, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
+  pstart();
   const int ks = k * S;
-  SC_LAUNCH(ctx, k_brow_count, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_cnt.p, cnt_n.p);
+  SC_TRY(b_off.ensure(ctx, (size_t)k + 1));
+  SC_TRY(bk_in.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(bk_out.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(bv_in.ensure(ctx, (size_t)ks + 1));
   SC_TRY(brow.ptr.ensure(ctx, (size_t)n + 1));
-  SC_TRY(brow.key.ensure(ctx, (size_t)ks));
-  SC_TRY(brow.val.ensure(ctx, (size_t)ks));
-  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, brow.ptr.p, (size_t)n + 1, tmp));
-  SC_LAUNCH(ctx, k_brow_fill, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_val.p, b_cnt.p, brow.ptr.p, cursor_n.p,
-            brow.key.p, brow.val.p);
-  SC_LAUNCH(ctx, k_rows_sort_small, (n + 255) / 256, 256, 0, n, brow.ptr.p, cnt_n.p, brow.key.p, brow.val.p);
-  RowLists Bl{brow.ptr.p, cnt_n.p, brow.key.p, brow.val.p};
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, Y, sp, hash_cap));
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Y.view(), KB, sp, hash_cap));
+  SC_TRY(brow.len.ensure(ctx, (size_t)n + 1));
+  SC_TRY(brow.key.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(brow.val.ensure(ctx, (size_t)ks + 1));
+  SC_CUDA(ctx, cudaMemcpyAsync(cnt_k.p, b_cnt.p, sizeof(int) * (size_t)k, cudaMemcpyDeviceToDevice, ctx->stream));
+  SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p + k, 0, sizeof(int), ctx->stream));
+  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_k.p, b_off.p, (size_t)k + 1, tmp));
+  long long bnnz = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&bnnz, b_off.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_LAUNCH(ctx, k_emit_b_pairs, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_val.p, b_cnt.p, b_off.p, bk_in.p, bv_in.p);
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int nbits = 1;
+  while ((1ll << nbits) < n) nbits++;
+  SC_TRY(sc_sort_pairs_u64_f64(ctx, bk_in.p, bk_out.p, bv_in.p, brow.val.p, (size_t)bnnz, 32 + nbits, tmp));
+  const long long span = std::max<long long>(bnnz, (long long)n + 1);
+  SC_LAUNCH(ctx, k_lists_from_sorted, (unsigned)((span + 255) / 256), 256, 0, n, bnnz, bk_out.p, brow.ptr.p, brow.len.p,
+            brow.key.p);
+  RowLists Bl = brow.view();
+  pstop(P_BROW);
+  pstart();
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, k, Y, sp));
+  pstop(P_SPGEMM_Y);
+  pstart();
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Y.view(), k, KB, sp));
+  pstop(P_SPGEMM_KB);
   return SC_OK;
 }
 
@@ -831,8 +1075,10 @@ int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
   SC_TRY(compute_KB());
+  pstart();
   SC_CUDA(ctx, cudaMemsetAsync(t1A.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
   SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p, KB.view(), t1A.p);
+  pstop(P_T1A);
   pre_valid = true;
   return SC_OK;
 }
@@ -860,11 +1106,10 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   g.slow_cnt = slow_cnt.p;
   SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
   int nslow = 0;
+  pstart();
   if (l2 == 0.0) {
-    constexpr size_t PER_WARP =
-        (size_t)(2 * FWA_NC + FWA_TCAP) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
     int grid = std::min((n + FWA_WARPS - 1) / FWA_WARPS, 148 * 16);
-    SC_LAUNCH(ctx, k_updateA_fast, grid, FWA_WARPS * 32, PER_WARP * FWA_WARPS, g);
+    SC_LAUNCH(ctx, k_updateA_fast, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
     SC_CUDA(ctx, cudaMemcpyAsync(&nslow, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   } else {
@@ -876,10 +1121,13 @@ int sc_fit::update_A(double l2, int* trace_dev) {
     nslow = n;
   }
   last_slow_cells = nslow;
+  pstop(P_UPDA_FAST);
+  pstart();
   if (nslow > 0) {
     int grid = std::min((nslow + 3) / 4, 148 * 16);
     SC_LAUNCH(ctx, k_updateA_slow, grid, 128, 0, g, nslow);
   }
+  pstop(P_UPDA_SLOW);
   a_cur = nxt;
   a_is_slots = true;
   return SC_OK;
@@ -891,6 +1139,7 @@ int sc_fit::update_B(int* trace_dev) {
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   const int cur = a_cur;
   // ---- t1B = A A^T: transpose A by a stable sort on (archetype, cell), then accumulate rows in cell order
+  pstart();
   SC_TRY(a_off.ensure(ctx, (size_t)n + 1));
   SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, a_cnt[cur].p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
   SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));
@@ -910,25 +1159,84 @@ int sc_fit::update_B(int* trace_dev) {
   SC_TRY(sc_sort_pairs_u64_f64(ctx, gk_in.p, gk_out.p, gv_in.p, gv_out.p, (size_t)annz, 32 + kbits, tmp));
   SC_LAUNCH(ctx, k_row_bounds, (k + 256) / 256, 256, 0, k, gk_out.p, annz, arow_ptr.p);
   SC_CUDA(ctx, cudaMemsetAsync(t1B.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
-  SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,
-            a_val[cur].p, a_cnt[cur].p, t1B.p);
+  {
+    // hub rows: found on the host from the row pointers (k+1 values)
+    const long long hub_thr = 8192;
+    std::vector<long long> hptr((size_t)k + 1);
+    SC_CUDA(ctx, cudaMemcpyAsync(hptr.data(), arow_ptr.p, sizeof(long long) * ((size_t)k + 1), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> hubs;
+    std::vector<unsigned char> ishub(k, 0);
+    for (int a = 0; a < k; ++a)
+      if (hptr[a + 1] - hptr[a] > hub_thr) {
+        hubs.push_back(a);
+        ishub[a] = 1;
+      }
+    last_hubs = (int)hubs.size();
+    SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, hub_thr, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,
+              a_val[cur].p, a_cnt[cur].p, t1B.p);
+    if (!hubs.empty()) {
+      const int H = (int)hubs.size();
+      SC_TRY(hub_list.ensure(ctx, (size_t)H));
+      SC_TRY(hub_flag.ensure(ctx, (size_t)k));
+      SC_CUDA(ctx, cudaMemcpyAsync(hub_list.p, hubs.data(), sizeof(int) * H, cudaMemcpyHostToDevice, ctx->stream));
+      SC_CUDA(ctx, cudaMemcpyAsync(hub_flag.p, ishub.data(), (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+      SC_LAUNCH(ctx, k_gram_mirror, dim3((k + 255) / 256, H), 256, 0, k, H, hub_list.p, hub_flag.p, t1B.p);
+      SC_LAUNCH(ctx, k_gram_hubpair, H * (H + 1) / 2, 256, 0, k, S, H, hub_list.p, arow_ptr.p, gk_out.p, gv_out.p,
+                a_idx[cur].p, a_val[cur].p, a_cnt[cur].p, t1B.p);
+      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+    }
+  }
+  pstop(P_GRAM);
   // ---- t2 = K A^T as per-cell rows, then as per-archetype candidate lists
+  pstart();
   RowLists Al{slot_ptr_n.p, a_cnt[cur].p, a_idx[cur].p, a_val[cur].p};
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, MA, sp, hash_cap));
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, MA.view(), T2c, sp, hash_cap));
-  SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p, 0, sizeof(int) * ((size_t)k + 1), ctx->stream));
-  SC_LAUNCH(ctx, k_count_keys, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, T2c.view(), cnt_k.p);
-  SC_TRY(c_ptr.ensure(ctx, (size_t)k + 1));
-  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_k.p, c_ptr.p, (size_t)k + 1, tmp));
-  long long cnnz = 0;
-  SC_CUDA(ctx, cudaMemcpyAsync(&cnnz, c_ptr.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp));
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, MA.view(), k, T2c, sp));
+  pstop(P_T2ROWS);
+  pstart();
+  {
+    SC_TRY(t_off.ensure(ctx, (size_t)n + 1));
+    SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, T2c.len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));
+    SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, t_off.p, (size_t)n + 1, tmp));
+    long long cnnz = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&cnnz, t_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cnnz >= (1ll << 32)) SC_FAIL(ctx, SC_ERR_CAPACITY, "update_B: more than 2^32 candidate pairs");
+    last_t2_nnz = cnnz;
+    SC_TRY(ck_in.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(ck_out.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(co_in.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(co_out.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(c_cellv.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(c_t2v.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(c_cell.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(c_t2.ensure(ctx, (size_t)cnnz + 1));
+    SC_TRY(c_ptr.ensure(ctx, (size_t)k + 1));
+    SC_LAUNCH(ctx, k_emit_cand, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, T2c.view(), t_off.p, ck_in.p,
+              co_in.p, c_cellv.p, c_t2v.p);
+    SC_TRY(sc_sort_pairs_u64_u32(ctx, ck_in.p, ck_out.p, co_in.p, co_out.p, (size_t)cnnz, 32 + kbits, tmp));
+    SC_LAUNCH(ctx, k_row_bounds, (k + 256) / 256, 256, 0, k, ck_out.p, cnnz, c_ptr.p);
+    SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
+              c_t2.p);
+  }
+  // chunk table: hub archetypes are spread over many CTAs
+  SC_TRY(chunk_ptr.ensure(ctx, (size_t)k + 1));
+  SC_LAUNCH(ctx, k_chunk_count, (k + 256) / 256, 256, 0, k, c_ptr.p, cnt_k.p);
+  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_k.p, chunk_ptr.p, (size_t)k + 1, tmp));
+  long long nchunks = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&nchunks, chunk_ptr.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  last_t2_nnz = cnnz;
-  SC_TRY(c_cell.ensure(ctx, (size_t)cnnz + 1));
-  SC_TRY(c_t2.ensure(ctx, (size_t)cnnz + 1));
-  SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p, 0, sizeof(int) * ((size_t)k + 1), ctx->stream));
-  SC_LAUNCH(ctx, k_scatter_by_key, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, T2c.view(), c_ptr.p, cnt_k.p,
-            c_cell.p, c_t2.p);
+  SC_TRY(chunk_arch.ensure(ctx, (size_t)nchunks + 1));
+  SC_TRY(cmax_v.ensure(ctx, (size_t)n));
+  SC_TRY(cmax_l.ensure(ctx, (size_t)n));
+  SC_TRY(bound_v.ensure(ctx, (size_t)2 * k));
+  SC_TRY(part_v.ensure(ctx, (size_t)nchunks + 1));
+  SC_TRY(part_i.ensure(ctx, (size_t)nchunks + 1));
+  SC_LAUNCH(ctx, k_chunk_fill, k, 128, 0, k, chunk_ptr.p, chunk_arch.p);
+  pstop(P_T2TRANS);
   // ---- T Frank-Wolfe steps; K B is re-evaluated from the current B at every step (cpu.py:486)
   for (int t = 0; t < T; ++t) {
     SC_TRY(compute_KB());
@@ -947,7 +1255,16 @@ int sc_fit::update_B(int* trace_dev) {
     g.b_val = b_val.p;
     g.b_cnt = b_cnt.p;
     g.trace = trace_dev;
-    SC_LAUNCH(ctx, k_updateB_iter, k, 256, 0, g);
+    pstart();
+    if (nchunks > 0) {
+      SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
+      SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
+                bound_v.p);
+      SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
+                part_v.p, part_i.p, bound_v.p);
+    }
+    SC_LAUNCH(ctx, k_updateB_step, k, 256, 0, g, chunk_ptr.p, part_v.p, part_i.p, bound_v.p);
+    pstop(P_GEVAL);
   }
   pre_valid = false;
   return SC_OK;
@@ -957,12 +1274,14 @@ int sc_fit::rss(double* out_host) {
   if (!have_A || !a_is_slots) SC_FAIL(ctx, SC_ERR_STATE, "fit: A has not been computed");
   SC_TRY(precompute_A());
   const int cur = a_cur;
+  pstart();
   SC_LAUNCH(ctx, k_rss_cell, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, k, S, a_idx[cur].p, a_val[cur].p,
             a_cnt[cur].p, KB.view(), t1A.p, percell.p);
   SC_TRY(sc_sum_f64(ctx, percell.p, scalars.p, (size_t)n, tmp));
   double s = 0.0;
   SC_CUDA(ctx, cudaMemcpyAsync(&s, scalars.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  pstop(P_RSS);
   const double sq = m_fro2 + s;
   *out_host = std::sqrt(sq > 0.0 ? sq : 0.0);
   return SC_OK;

@@ -8,7 +8,6 @@
 struct sc_fit {
   sc_ctx* ctx = nullptr;
   int n = 0, k = 0, T = 50, S = 50;
-  int hash_cap = 512;
   // kernel matrix M
   DBuf<int> m_ptr, m_col;
   DBuf<double> m_val;
@@ -26,20 +25,37 @@ struct sc_fit {
   DBuf<double> b_val;
   // B by cell, M*B, K*B
   RowListsBuf brow, Y, KB;
+  DBuf<long long> b_off;
+  DBuf<unsigned long long> bk_in, bk_out;
+  DBuf<double> bv_in;
   DBuf<double> t1A, t1B;
   // _updateB precompute
   RowListsBuf MA, T2c;
-  DBuf<long long> c_ptr, a_off, arow_ptr;
+  DBuf<long long> c_ptr, a_off, arow_ptr, chunk_ptr, t_off;
+  DBuf<unsigned long long> ck_in, ck_out;
+  DBuf<unsigned> co_in, co_out;
+  DBuf<int> c_cellv;
+  DBuf<double> c_t2v;
+  DBuf<int> chunk_arch, part_i, hub_list;
+  DBuf<double> part_v, cmax_v, bound_v;
+  DBuf<int> cmax_l;
+  DBuf<unsigned char> hub_flag;
+  int last_hubs = 0;
   DBuf<int> c_cell;
   DBuf<double> c_t2;
   DBuf<unsigned long long> gk_in, gk_out;
   DBuf<double> gv_in, gv_out;
   // scratch
-  DBuf<int> cnt_n, cnt_k, cursor_n, slow_list, slow_cnt;
+  DBuf<int> cnt_n, cnt_k, slow_list, slow_cnt;
   DBuf<double> percell, scalars;
   SpgemmScratch sp;
   DBuf<char> tmp;
   // diagnostics
+  bool profile = false;      // SC_PROFILE=1: synchronise around every stage and accumulate wall seconds
+  double prof[16] = {0};
+  double prof_t0 = 0.0;
+  void pstart();
+  void pstop(int stage);
   int last_slow_cells = 0;
   long long last_t2_nnz = 0;
 

@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "spgemm_rows.cuh"
 
+#include <algorithm>
+
 __global__ void k_spgemm_ub(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
                             const int* __restrict__ x_len, long long* __restrict__ ub, int nrows_total) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,7 +30,8 @@ template <int CAP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
               const double* __restrict__ s_val, RowLists X, const long long* __restrict__ z_ptr,
-              int* __restrict__ z_len, int* __restrict__ z_key, double* __restrict__ z_val, int* __restrict__ flags) {
+              int* __restrict__ z_len, int* __restrict__ z_key, double* __restrict__ z_val, int* __restrict__ flags,
+              int* __restrict__ big_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* tvals = reinterpret_cast<double*>(smem_raw) + (size_t)warp * CAP;
@@ -122,9 +125,9 @@ k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const i
         }
       }
     }
-    if (overflow) {
+    if (overflow) {  // too many distinct keys for the shared-memory table: hand the row to k_spgemm_big
       if (lane == 0) {
-        atomicExch(&flags[0], 1);
+        big_list[atomicAdd(&flags[0], 1)] = i;
         z_len[i] = 0;
       }
       __syncwarp();
@@ -179,34 +182,77 @@ k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const i
   }
 }
 
-template <int CAP, int WARPS>
-static int launch_fill(sc_ctx* ctx, int row_begin, int row_end, const CsrView& S, const RowLists& X, RowListsBuf& Z,
-                       int* flags) {
-  const size_t smem = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+// Rows with more distinct keys than the shared-memory table holds (cells next to a "hub" cell that many archetypes
+// put weight on - a by-product of the reference's argmin-of-zeros rule): one CTA per row, dense accumulator over the
+// whole key space in global scratch.  Keys of one X row are distinct, X rows are applied one after the other, so the
+// accumulation order is again fixed; the output comes out sorted by key without a sort.
+constexpr int BIG_THREADS = 256;
+__global__ void __launch_bounds__(BIG_THREADS)
+k_spgemm_big(int nbig, const int* __restrict__ big_list, int key_space, const int* __restrict__ s_ptr,
+             const int* __restrict__ s_col, const double* __restrict__ s_val, RowLists X,
+             const long long* __restrict__ z_ptr, int* __restrict__ z_len, int* __restrict__ z_key,
+             double* __restrict__ z_val, double* __restrict__ scratch) {
+  __shared__ int wtot[BIG_THREADS / 32];
+  __shared__ int s_running;
+  double* acc = scratch + (size_t)blockIdx.x * key_space;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
+    const int i = big_list[w];
+    for (int t = tid; t < key_space; t += BIG_THREADS) acc[t] = 0.0;
+    __syncthreads();
+    for (int p = s_ptr[i]; p < s_ptr[i + 1]; ++p) {
+      const int q = s_col[p];
+      const double m = s_val[p];
+      const long long xp = X.ptr[q];
+      const int xl = X.len[q];
+      for (int x = tid; x < xl; x += BIG_THREADS) {
+        const int key = X.key[xp + x];
+        acc[key] = __dadd_rn(acc[key], __dmul_rn(m, X.val[xp + x]));
+      }
+      __syncthreads();
+    }
+    if (tid == 0) s_running = 0;
+    __syncthreads();
+    const long long zp = z_ptr[i];
+    for (int base = 0; base < key_space; base += BIG_THREADS) {
+      const int t = base + tid;
+      const double v = (t < key_space) ? acc[t] : 0.0;
+      const bool occ = v != 0.0;
+      const unsigned ball = __ballot_sync(0xffffffffu, occ);
+      if (lane == 0) wtot[warp] = __popc(ball);
+      __syncthreads();
+      int before = s_running;
+      for (int ww = 0; ww < warp; ++ww) before += wtot[ww];
+      if (occ) {
+        const int pos = before + __popc(ball & ((1u << lane) - 1u));
+        z_key[zp + pos] = t;
+        z_val[zp + pos] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int ww = 0; ww < BIG_THREADS / 32; ++ww) tot += wtot[ww];
+        s_running += tot;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) z_len[i] = s_running;
+    __syncthreads();
   }
-  const int rows = row_end - row_begin;
-  if (rows <= 0) return SC_OK;
-  int grid = (rows + WARPS - 1) / WARPS;
-  const int maxgrid = 148 * 16;
-  if (grid > maxgrid) grid = maxgrid;
-  SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
-            X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, flags);
-  return SC_OK;
 }
 
-int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, RowListsBuf& Z,
-                   SpgemmScratch& sc, int hash_cap) {
+int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
+                   RowListsBuf& Z, SpgemmScratch& sc) {
+  constexpr int CAP = 512, WARPS = 8;
   const int n = S.n;
   SC_TRY(sc.ub.ensure(ctx, (size_t)n + 1));
   SC_TRY(Z.ptr.ensure(ctx, (size_t)n + 1));
   SC_TRY(Z.len.ensure(ctx, (size_t)n));
   SC_TRY(sc.flags.ensure(ctx, 4));
+  SC_TRY(sc.big_list.ensure(ctx, (size_t)n));
   Z.rows = n;
   SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+  SC_CUDA(ctx, cudaMemsetAsync(sc.flags.p, 0, sizeof(int) * 4, ctx->stream));
   SC_LAUNCH(ctx, k_spgemm_ub, (n + 1 + 255) / 256, 256, 0, row_begin, row_end, S.indptr, S.indices, X.len, sc.ub.p, n);
   SC_TRY(sc_exclusive_scan_i64(ctx, sc.ub.p, Z.ptr.p, (size_t)n + 1, sc.tmp));
   long long total = 0;
@@ -214,22 +260,26 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   SC_TRY(Z.key.ensure(ctx, (size_t)total + 1));
   SC_TRY(Z.val.ensure(ctx, (size_t)total + 1));
-  while (true) {
-    SC_CUDA(ctx, cudaMemsetAsync(sc.flags.p, 0, sizeof(int) * 4, ctx->stream));
-    if (hash_cap <= 512) {
-      SC_TRY((launch_fill<512, 8>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
-    } else if (hash_cap <= 4096) {
-      SC_TRY((launch_fill<4096, 2>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
-    } else {
-      SC_TRY((launch_fill<16384, 1>(ctx, row_begin, row_end, S, X, Z, sc.flags.p)));
-    }
-    int flag = 0;
-    SC_CUDA(ctx, cudaMemcpyAsync(&flag, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!flag) break;
-    if (hash_cap <= 512) hash_cap = 4096;
-    else if (hash_cap <= 4096) hash_cap = 16384;
-    else SC_FAIL(ctx, SC_ERR_CAPACITY, "spgemm_rows: a row has more than 14336 distinct archetypes");
+  const int rows = row_end - row_begin;
+  if (rows <= 0) return SC_OK;
+  const size_t smem = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int grid = std::min((rows + WARPS - 1) / WARPS, 148 * 16);
+  SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
+            X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+  int nbig = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&nbig, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  sc.last_big_rows = nbig;
+  if (nbig > 0) {
+    const int bgrid = std::min(nbig, 148 * 2);
+    SC_TRY(sc.big_acc.ensure(ctx, (size_t)bgrid * key_space));
+    SC_LAUNCH(ctx, k_spgemm_big, bgrid, BIG_THREADS, 0, nbig, sc.big_list.p, key_space, S.indptr, S.indices, S.data, X,
+              Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.big_acc.p);
   }
   return SC_OK;
 }

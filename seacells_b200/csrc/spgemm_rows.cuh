@@ -3,10 +3,13 @@
 
 struct SpgemmScratch {
   DBuf<long long> ub;
-  DBuf<int> flags;
+  DBuf<int> flags, big_list;
+  DBuf<double> big_acc;
   DBuf<char> tmp;
+  int last_big_rows = 0;
 };
 
 // Z[i,:] = sum_q S[i,q] * X[q,:] for rows i in [row_begin,row_end); other rows of Z are empty.  Rows sorted by key.
-int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, RowListsBuf& Z,
-                   SpgemmScratch& sc, int hash_cap = 512);
+// key_space: keys of X are in [0, key_space).
+int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
+                   RowListsBuf& Z, SpgemmScratch& sc);

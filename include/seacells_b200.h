@@ -108,8 +108,11 @@ int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells /* [k] */);
 int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
 /* diagnostics: [0] cells that took the generic path in the last _updateA, [1] nnz(t2) of the last _updateB,
  * [2] hub archetypes (rows of A longer than 8192 cells) in the last _updateB, [3] rows of the last K*B product that
- * needed the dense-accumulator kernel */
-int sc_fit_stats(sc_fit* fit, long long* out4);
+ * needed the dense-accumulator kernel, [4] (cell, archetype) gradients evaluated exactly in the last _updateB (all
+ * Frank-Wolfe steps together; the rest of nnz(t2) x max_FW_iter was pruned by the lower bounds), [5] Frank-Wolfe
+ * steps of _updateB timed so far and [6] their summed CUDA-event time in ns for the gradient kernel (row max + both
+ * rounds of k_updateB_eval), [7] nnz of the last K*B row lists.  out: 8 values. */
+int sc_fit_stats(sc_fit* fit, long long* out8);
 /* with SC_PROFILE=1 in the environment: accumulated wall seconds per stage (synchronising; development aid).
  * [0] B-by-cell [1] M*B [2] M*(M*B) [3] t1=B^T K B [4] _updateA shared-memory path [5] _updateA generic path
  * [6] A A^T [7] K A^T rows [8] candidates by archetype [9] _updateB gradient+argmin+step [10] RSS */

@@ -360,6 +360,10 @@ int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w) {
 }
 int sc_fit_stats(sc_fit* fit, long long* out4) {
   if (!fit || !out4) return SC_ERR_ARG;
+  out4[4] = fit->last_evaluated;
+  out4[5] = fit->eval_steps;
+  out4[6] = (long long)(fit->eval_ms_total * 1e6);  /* ns */
+  out4[7] = fit->last_kb_nnz;
   out4[0] = fit->last_slow_cells;
   out4[1] = fit->last_t2_nnz;
   out4[2] = fit->last_hubs;

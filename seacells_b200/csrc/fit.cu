@@ -27,6 +27,14 @@ __global__ void k_fill_stride_ptr(long long* p, int rows, int stride) {
   if (r <= rows) p[r] = (long long)r * stride;
 }
 
+__global__ void k_sum_len(int rows, const int* __restrict__ len, unsigned long long* out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = (r < rows) ? (unsigned long long)len[r] : 0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 __global__ void k_square(const double* __restrict__ in, double* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] * in[i];
@@ -525,6 +533,7 @@ struct UpdBArgs {
   double* b_val;
   int* b_cnt;
   int* trace;  // [T * k] or null
+  unsigned long long* evaluated;  // diagnostics: candidates whose exact gradient was computed
 };
 
 constexpr int UPB_CHUNK = 1024;  // candidates per CTA
@@ -622,28 +631,57 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   const double bound = (round == 0) ? FW_INF : bound_v[a];
   const int e_begin = (round == 1 && chunk == 0) ? 256 : 0;
   const int e_end = (round == 0) ? min(nc, 256) : nc;
+  // phase 1: cheap bound tests, survivors compacted into shared memory
+  __shared__ int q_cell[UPB_CHUNK];
+  __shared__ double q_t2[UPB_CHUNK];
+  __shared__ int q_n;
+  if (threadIdx.x == 0) q_n = 0;
+  __syncthreads();
+  for (int e0 = e_begin; e0 < e_end; e0 += 256) {
+    const int e = e0 + threadIdx.x;
+    int cell = 0;
+    double t2v = 0.0;
+    bool live = false;
+    if (e < e_end) {
+      t2v = g.c_t2[c0 + e];
+      live = !(-2.0 * t2v > bound);
+      if (live) {
+        cell = g.c_cell[c0 + e];
+        if (round == 1) {
+          const double hb = __dmul_rn(cmax_v[cell], row[cmax_l[cell]]);
+          live = !(2.0 * (hb - t2v) > bound);
+        }
+      }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, live);
+    int wbase = 0;
+    if (lane == 0 && ball) wbase = atomicAdd(&q_n, __popc(ball));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (live) {
+      const int pos = wbase + __popc(ball & ((1u << lane) - 1u));
+      q_cell[pos] = cell;
+      q_t2[pos] = t2v;
+    }
+  }
+  __syncthreads();
+  const int nq = q_n;
+  if (threadIdx.x == 0 && g.evaluated) atomicAdd(g.evaluated, (unsigned long long)nq);
+  // phase 2: exact gradient of the survivors, one per thread
   double bv = FW_INF;
   int bi = 0x7fffffff;
-  for (int e0 = e_begin; e0 < e_end; e0 += 256) {
+  for (int e0 = 0; e0 < nq; e0 += 256) {
     const int e = e0 + threadIdx.x;
     int cell = 0, L = 0;
     long long p = 0;
     double t2v = 0.0;
     bool live = false;
-    if (e < e_end) {
-      t2v = g.c_t2[c0 + e];
-      const double cut = fmin(bound, bv);
-      live = !(-2.0 * t2v > cut);
+    if (e < nq) {
+      cell = q_cell[e];
+      t2v = q_t2[e];
+      live = !(-2.0 * t2v > bv);  // the thread's own running minimum tightens the first bound further
       if (live) {
-        cell = g.c_cell[c0 + e];
-        if (round == 1) {
-          const double hb = __dmul_rn(cmax_v[cell], row[cmax_l[cell]]);
-          live = !(2.0 * (hb - t2v) > cut);
-        }
-        if (live) {
-          p = g.KB.ptr[cell];
-          L = g.KB.len[cell];
-        }
+        p = g.KB.ptr[cell];
+        L = g.KB.len[cell];
       }
     }
     if (live && L <= UPB_LONG) {
@@ -917,6 +955,11 @@ static int set_smem_attr_once(sc_ctx* ctx) {
                                     (int)(FWA_PER_WARP * FWA_WARPS)));
   done = true;
   return SC_OK;
+}
+
+sc_fit::~sc_fit() {
+  for (auto e : ev_a) cudaEventDestroy(e);
+  for (auto e : ev_b) cudaEventDestroy(e);
 }
 
 int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
@@ -1233,6 +1276,8 @@ int sc_fit::update_B(int* trace_dev) {
   SC_TRY(cmax_v.ensure(ctx, (size_t)n));
   SC_TRY(cmax_l.ensure(ctx, (size_t)n));
   SC_TRY(bound_v.ensure(ctx, (size_t)2 * k));
+  SC_TRY(eval_cnt.ensure(ctx, 2));
+  SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p, 0, sizeof(unsigned long long) * 2, ctx->stream));
   SC_TRY(part_v.ensure(ctx, (size_t)nchunks + 1));
   SC_TRY(part_i.ensure(ctx, (size_t)nchunks + 1));
   SC_LAUNCH(ctx, k_chunk_fill, k, 128, 0, k, chunk_ptr.p, chunk_arch.p);
@@ -1255,7 +1300,16 @@ int sc_fit::update_B(int* trace_dev) {
     g.b_val = b_val.p;
     g.b_cnt = b_cnt.p;
     g.trace = trace_dev;
+    g.evaluated = eval_cnt.p;
     pstart();
+    if ((int)ev_a.size() <= t) {
+      cudaEvent_t ea, eb;
+      SC_CUDA(ctx, cudaEventCreate(&ea));
+      SC_CUDA(ctx, cudaEventCreate(&eb));
+      ev_a.push_back(ea);
+      ev_b.push_back(eb);
+    }
+    SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
     if (nchunks > 0) {
       SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
       SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
@@ -1263,8 +1317,27 @@ int sc_fit::update_B(int* trace_dev) {
       SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
                 part_v.p, part_i.p, bound_v.p);
     }
+    SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
     SC_LAUNCH(ctx, k_updateB_step, k, 256, 0, g, chunk_ptr.p, part_v.p, part_i.p, bound_v.p);
     pstop(P_GEVAL);
+  }
+  {
+    unsigned long long ev = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&ev, eval_cnt.p, sizeof(ev), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    last_evaluated = (long long)ev;
+    for (int t = 0; t < T; ++t) {
+      float ms = 0.f;
+      SC_CUDA(ctx, cudaEventElapsedTime(&ms, ev_a[t], ev_b[t]));
+      eval_ms_total += ms;
+      eval_steps++;
+    }
+    long long kbn = 0;  // nnz(K B) of the last Frank-Wolfe step
+    SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p + 1, 0, sizeof(unsigned long long), ctx->stream));
+    SC_LAUNCH(ctx, k_sum_len, (n + 255) / 256, 256, 0, n, KB.len.p, eval_cnt.p + 1);
+    SC_CUDA(ctx, cudaMemcpyAsync(&kbn, eval_cnt.p + 1, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    last_kb_nnz = kbn;
   }
   pre_valid = false;
   return SC_OK;

@@ -41,6 +41,14 @@ struct sc_fit {
   DBuf<int> cmax_l;
   DBuf<unsigned char> hub_flag;
   int last_hubs = 0;
+  DBuf<unsigned long long> eval_cnt;
+  long long last_evaluated = 0;
+  // CUDA-event timing of the dominant kernel (k_updateB_eval, both rounds of one Frank-Wolfe step), always on
+  std::vector<cudaEvent_t> ev_a, ev_b;
+  double eval_ms_total = 0.0;
+  long long eval_steps = 0;
+  long long last_kb_nnz = 0;
+  ~sc_fit();
   DBuf<int> c_cell;
   DBuf<double> c_t2;
   DBuf<unsigned long long> gk_in, gk_out;

@@ -88,6 +88,24 @@ int sc_fit_set_B_slots(sc_fit* fit, const int32_t* idx, const double* val, const
 int sc_fit_update_A(sc_fit* fit, double l2_penalty, int32_t* trace);
 /* _updateB (cpu.py:461-498).  trace: NULL or host int32 [max_FW_iter x k]. */
 int sc_fit_update_B(sc_fit* fit, int32_t* trace);
+/* ---- multi-GPU (one process per GPU; cells sharded by contiguous slabs) ---------------------------
+ * The library never communicates: the host (torch.distributed / NCCL) moves two things between these calls.
+ *   sc_fit_set_shard      this rank owns cells [row_begin,row_end): _updateA fills only those columns of A, and the
+ *                         candidate lists / K*B rows of _updateB are built for those cells only.
+ *   sc_fit_A_slots_device device pointers of the current compressed A (idx int32 [rows,S], val fp64 [rows,S],
+ *                         cnt int32 [rows], rows = n+64 so equal slabs can be all-gathered in place) - all-gather them
+ *                         after every sc_fit_update_A.
+ *   _updateB in phases    begin (Gram, t2, candidates); then per Frank-Wolfe step t: eval writes this rank's
+ *                         per-archetype partial {cand min G, cell, non-candidate G, cell} (k x 4 fp64, device) -> the
+ *                         host all-gathers the partials -> step merges them and updates the replicated B; end.
+ *   sc_fit_update_B is exactly begin + T x (eval, step with n_ranks = 1) + end. */
+int sc_fit_set_shard(sc_fit* fit, int row_begin, int row_end);
+int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long long* rows_allocated);
+int sc_fit_update_B_begin(sc_fit* fit);
+int sc_fit_update_B_eval(sc_fit* fit, int t, double* partial_dev /* [k*4] device */);
+int sc_fit_update_B_step(sc_fit* fit, int t, const double* gathered_dev /* [n_ranks][k*4] device */, int n_ranks);
+int sc_fit_update_B_end(sc_fit* fit);
+
 /* compute_RSS (cpu.py:520-536): || M - (M B) A ||_F via the trace identity, no n x n product */
 int sc_fit_rss(sc_fit* fit, double* rss_out);
 /* initialize + _fit (cpu.py:204-285, 595-651) for already-set archetypes and A0.  threshold_inout: <= 0 on entry

@@ -47,6 +47,12 @@ SIGNATURES = {
     "sc_fit_update_A": (_i, [_vp, _d, _vp]),
     "sc_fit_update_B": (_i, [_vp, _vp]),
     "sc_fit_rss": (_i, [_vp, C.POINTER(_d)]),
+    "sc_fit_set_shard": (_i, [_vp, _i, _i]),
+    "sc_fit_A_slots_device": (_i, [_vp, _pp, _pp, _pp, C.POINTER(_ll)]),
+    "sc_fit_update_B_begin": (_i, [_vp]),
+    "sc_fit_update_B_eval": (_i, [_vp, _i, _vp]),
+    "sc_fit_update_B_step": (_i, [_vp, _i, _vp, _i]),
+    "sc_fit_update_B_end": (_i, [_vp]),
     "sc_fit_run": (_i, [_vp, _i, _i, _d, _d, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp, _i, C.POINTER(_i)]),
     "sc_fit_slots": (_i, [_vp]),
     "sc_fit_get_A": (_i, [_vp, _vp, _vp, _vp]),

@@ -323,6 +323,34 @@ int sc_fit_update_B(sc_fit* fit, int32_t* trace) {
   return with_trace(fit, trace, (size_t)fit->T * fit->k, [](sc_fit* f, int* t, double) { return f->update_B(t); }, 0.0);
 }
 
+int sc_fit_set_shard(sc_fit* fit, int row_begin, int row_end) {
+  if (!fit) return SC_ERR_ARG;
+  return fit->set_shard(row_begin, row_end);
+}
+
+int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long long* rows_allocated) {
+  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  if (!fit->have_A || !fit->a_is_slots) SC_FAIL(fit->ctx, SC_ERR_STATE, "fit: A has not been computed");
+  *idx = fit->a_idx[fit->a_cur].p;
+  *val = fit->a_val[fit->a_cur].p;
+  *cnt = fit->a_cnt[fit->a_cur].p;
+  if (rows_allocated) *rows_allocated = (long long)fit->n + 64;
+  return SC_OK;
+}
+
+int sc_fit_update_B_begin(sc_fit* fit) { return fit ? fit->update_B_begin() : SC_ERR_ARG; }
+int sc_fit_update_B_eval(sc_fit* fit, int t, double* partial_dev) {
+  if (!fit || !partial_dev) return SC_ERR_ARG;
+  if (!sc_is_device_ptr(partial_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_eval: partial buffer must be device memory");
+  return fit->update_B_eval(t, partial_dev);
+}
+int sc_fit_update_B_step(sc_fit* fit, int t, const double* gathered_dev, int n_ranks) {
+  if (!fit || !gathered_dev || n_ranks < 1) return SC_ERR_ARG;
+  if (!sc_is_device_ptr(gathered_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_step: gathered buffer must be device memory");
+  return fit->update_B_step(t, gathered_dev, n_ranks, nullptr);
+}
+int sc_fit_update_B_end(sc_fit* fit) { return fit ? fit->update_B_end() : SC_ERR_ARG; }
+
 int sc_fit_rss(sc_fit* fit, double* rss_out) {
   if (!fit || !rss_out) return SC_ERR_ARG;
   return fit->rss(rss_out);

@@ -726,17 +726,19 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   }
 }
 
-// Per archetype: reduce the chunk minima, apply the dense-column rule when nothing is negative, take the simplex step.
-__global__ void __launch_bounds__(256) k_updateB_step(UpdBArgs g, const long long* __restrict__ chunk_ptr,
-                                                      const double* __restrict__ part_v,
-                                                      const int* __restrict__ part_i,
-                                                      const double* __restrict__ bound_v) {
+// Per archetype, on the rank's own cells: reduce the chunk minima; if no local candidate is negative, scan the local
+// cells outside the support of t2 (their gradient is 2 (K B t1)[i,a] >= 0) in ascending order for the first exact zero.
+// out[a] = { candidate min G, its cell, non-candidate result G (0 for a zero, else the local minimum), its cell }.
+__global__ void __launch_bounds__(256) k_updateB_local(UpdBArgs g, int row_begin, int row_end,
+                                                       const long long* __restrict__ chunk_ptr,
+                                                       const double* __restrict__ part_v,
+                                                       const int* __restrict__ part_i,
+                                                       const double* __restrict__ bound_v, double* __restrict__ out) {
   __shared__ double sg[8];
   __shared__ int si[8];
   __shared__ int s_zero;
   const int a = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = g.k, S = g.S;
+  const int k = g.k;
   const double* __restrict__ row = g.t1 + (size_t)a * k;
   double bv = FW_INF;
   int bi = 0x7fffffff;
@@ -754,19 +756,16 @@ __global__ void __launch_bounds__(256) k_updateB_step(UpdBArgs g, const long lon
   }
   if (threadIdx.x == 0) s_zero = 0x7fffffff;
   block_argmin_256(bv, bi, sg, si);
-  int amin = bi;
+  double nv = FW_INF;
+  int ni = 0x7fffffff;
   const long long ncand = g.c_ptr[a + 1] - g.c_ptr[a];
-  if (!(bv < 0.0) && ncand < (long long)g.n) {
-    // No candidate is negative, so the column minimum is >= 0 and np.argmin returns the first exact zero if there is
-    // one.  Cells outside the support of t2 have G = 2 (K B t1)[i,a] >= 0: scan them in ascending order, stop at the
-    // first zero (or once past a candidate that is itself exactly zero); candidates were already evaluated above.
-    double tv = bv;
-    int ti = bi;
+  if (!(bv < 0.0) && ncand < (long long)(row_end - row_begin)) {
+    double tv = FW_INF;
+    int ti = 0x7fffffff;
     bool found = false;
-    const int stop_at = (bv == 0.0) ? bi : g.n;
-    for (int i0 = 0; i0 < stop_at; i0 += 256) {
+    for (int i0 = row_begin; i0 < row_end; i0 += 256) {
       const int i = i0 + threadIdx.x;
-      if (i < stop_at) {
+      if (i < row_end) {
         const long long tp = g.T2c.ptr[i];
         const int tl = g.T2c.len[i];
         int lo = 0, hi = tl;
@@ -794,17 +793,53 @@ __global__ void __launch_bounds__(256) k_updateB_step(UpdBArgs g, const long lon
       __syncthreads();  // everyone has read s_zero before the next chunk may lower it
       if (z != 0x7fffffff) {
         found = true;
-        amin = z;
+        nv = 0.0;
+        ni = z;
         break;
       }
     }
     if (!found) {
       block_argmin_256(tv, ti, sg, si);
-      amin = ti;
+      nv = tv;
+      ni = ti;
     }
   }
-  // simplex step on column a of B (cpu.py:494)
-  if (warp == 0) {
+  if (threadIdx.x == 0) {
+    out[(size_t)a * 4 + 0] = bv;
+    out[(size_t)a * 4 + 1] = (double)bi;
+    out[(size_t)a * 4 + 2] = nv;
+    out[(size_t)a * 4 + 3] = (double)ni;
+  }
+}
+
+// Merge the per-rank partials (gathered[r][a][4]) into the column argmin - negative candidate minimum if there is one,
+// else the first exact zero / first minimum over the whole column (np.argmin on the dense column) - and take the
+// simplex step on column a of B (cpu.py:487-494).  Every rank runs this on identical inputs, so B stays replicated.
+__global__ void __launch_bounds__(32) k_updateB_step(UpdBArgs g, const double* __restrict__ gathered, int n_ranks) {
+  const int a = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int k = g.k, S = g.S;
+  double cv = FW_INF, nv = FW_INF;
+  int ci = 0x7fffffff, ni = 0x7fffffff;
+  for (int r = 0; r < n_ranks; ++r) {
+    const double* e = gathered + ((size_t)r * k + a) * 4;
+    const double v0 = e[0], v2 = e[2];
+    const int i0 = (int)e[1], i2 = (int)e[3];
+    if (v0 < cv || (v0 == cv && i0 < ci)) {
+      cv = v0;
+      ci = i0;
+    }
+    if (v2 < nv || (v2 == nv && i2 < ni)) {
+      nv = v2;
+      ni = i2;
+    }
+  }
+  int amin = ci;
+  if (!(cv < 0.0)) {
+    if (nv < cv || (nv == cv && ni < ci)) amin = ni;
+    if (amin == 0x7fffffff) amin = 0;
+  }
+  {
     const int cnt = g.b_cnt[a];
     const double gamma = fw_gamma(g.t);
     int* bidx = g.b_idx + (size_t)a * S;
@@ -966,6 +1001,8 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
   profile = std::getenv("SC_PROFILE") != nullptr;
   n = n_;
+  row_begin = 0;
+  row_end = n_;
   k = k_;
   T = T_;
   S = std::max(T_, 1);
@@ -974,9 +1011,9 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   SC_TRY(slot_ptr_n.ensure(ctx, (size_t)n + 1));
   SC_LAUNCH(ctx, k_fill_stride_ptr, (n + 256) / 256, 256, 0, slot_ptr_n.p, n, S);
   for (int b = 0; b < 2; ++b) {
-    SC_TRY(a_idx[b].ensure(ctx, (size_t)n * S));
-    SC_TRY(a_val[b].ensure(ctx, (size_t)n * S));
-    SC_TRY(a_cnt[b].ensure(ctx, (size_t)n));
+    SC_TRY(a_idx[b].ensure(ctx, ((size_t)n + 64) * S));  // + padding rows so equal slabs can be all-gathered in place
+    SC_TRY(a_val[b].ensure(ctx, ((size_t)n + 64) * S));
+    SC_TRY(a_cnt[b].ensure(ctx, (size_t)n + 64));
   }
   SC_TRY(b_idx.ensure(ctx, (size_t)k * S));
   SC_TRY(b_val.ensure(ctx, (size_t)k * S));
@@ -1077,7 +1114,7 @@ RowLists sc_fit::A_view() const {
 }
 
 // KB rows and t1A for the current B (shared by _updateA and compute_RSS)
-int sc_fit::compute_KB() {
+int sc_fit::compute_KB(int r0, int r1) {
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   // B by cell
   pstart();
@@ -1109,7 +1146,7 @@ int sc_fit::compute_KB() {
   SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, k, Y, sp));
   pstop(P_SPGEMM_Y);
   pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Y.view(), k, KB, sp));
+  SC_TRY(sc_spgemm_rows(ctx, M, r0, r1, Y.view(), k, KB, sp));
   pstop(P_SPGEMM_KB);
   return SC_OK;
 }
@@ -1117,7 +1154,7 @@ int sc_fit::compute_KB() {
 int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
-  SC_TRY(compute_KB());
+  SC_TRY(compute_KB(0, n));  // all rows: t1 and the RSS need K B at every cell (replicated across ranks)
   pstart();
   SC_CUDA(ctx, cudaMemsetAsync(t1A.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
   SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p, KB.view(), t1A.p);
@@ -1131,8 +1168,8 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   SC_TRY(precompute_A());
   const int nxt = (a_cur < 0) ? 0 : 1 - a_cur;
   UpdAArgs g;
-  g.cell_begin = 0;
-  g.cell_end = n;
+  g.cell_begin = row_begin;
+  g.cell_end = row_end;
   g.n = n;
   g.k = k;
   g.S = S;
@@ -1151,17 +1188,18 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   int nslow = 0;
   pstart();
   if (l2 == 0.0) {
-    int grid = std::min((n + FWA_WARPS - 1) / FWA_WARPS, 148 * 16);
+    int grid = std::min((row_end - row_begin + FWA_WARPS - 1) / FWA_WARPS, 148 * 16);
     SC_LAUNCH(ctx, k_updateA_fast, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
     SC_CUDA(ctx, cudaMemcpyAsync(&nslow, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   } else {
     // the -l2*A term can make entries outside the support of t2 negative: every cell takes the generic path
-    std::vector<int> all(n);
-    for (int j = 0; j < n; ++j) all[j] = j;
-    SC_CUDA(ctx, sc_copy(slow_list.p, all.data(), sizeof(int) * (size_t)n, ctx->stream));
+    const int nloc = row_end - row_begin;
+    std::vector<int> all(nloc);
+    for (int j = 0; j < nloc; ++j) all[j] = row_begin + j;
+    SC_CUDA(ctx, sc_copy(slow_list.p, all.data(), sizeof(int) * (size_t)nloc, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    nslow = n;
+    nslow = nloc;
   }
   last_slow_cells = nslow;
   pstop(P_UPDA_FAST);
@@ -1176,7 +1214,7 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   return SC_OK;
 }
 
-int sc_fit::update_B(int* trace_dev) {
+int sc_fit::update_B_begin() {
   if (!have_A || !a_is_slots) SC_FAIL(ctx, SC_ERR_STATE, "fit: run update_A before update_B");
   if (!have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: B has not been initialised");
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
@@ -1236,7 +1274,7 @@ int sc_fit::update_B(int* trace_dev) {
   pstart();
   RowLists Al{slot_ptr_n.p, a_cnt[cur].p, a_idx[cur].p, a_val[cur].p};
   SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp));
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, MA.view(), k, T2c, sp));
+  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MA.view(), k, T2c, sp));  // candidates: this rank's cells only
   pstop(P_T2ROWS);
   pstart();
   {
@@ -1282,45 +1320,82 @@ int sc_fit::update_B(int* trace_dev) {
   SC_TRY(part_i.ensure(ctx, (size_t)nchunks + 1));
   SC_LAUNCH(ctx, k_chunk_fill, k, 128, 0, k, chunk_ptr.p, chunk_arch.p);
   pstop(P_T2TRANS);
-  // ---- T Frank-Wolfe steps; K B is re-evaluated from the current B at every step (cpu.py:486)
-  for (int t = 0; t < T; ++t) {
-    SC_TRY(compute_KB());
-    UpdBArgs g;
-    g.n = n;
-    g.k = k;
-    g.S = S;
-    g.t = t;
-    g.t1 = t1B.p;
-    g.c_ptr = c_ptr.p;
-    g.c_cell = c_cell.p;
-    g.c_t2 = c_t2.p;
-    g.KB = KB.view();
-    g.T2c = T2c.view();
-    g.b_idx = b_idx.p;
-    g.b_val = b_val.p;
-    g.b_cnt = b_cnt.p;
-    g.trace = trace_dev;
-    g.evaluated = eval_cnt.p;
-    pstart();
-    if ((int)ev_a.size() <= t) {
-      cudaEvent_t ea, eb;
-      SC_CUDA(ctx, cudaEventCreate(&ea));
-      SC_CUDA(ctx, cudaEventCreate(&eb));
-      ev_a.push_back(ea);
-      ev_b.push_back(eb);
-    }
-    SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
-    if (nchunks > 0) {
-      SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
-      SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
-                bound_v.p);
-      SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
-                part_v.p, part_i.p, bound_v.p);
-    }
-    SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
-    SC_LAUNCH(ctx, k_updateB_step, k, 256, 0, g, chunk_ptr.p, part_v.p, part_i.p, bound_v.p);
-    pstop(P_GEVAL);
+  nchunks_cur = nchunks;
+  SC_TRY(part_out.ensure(ctx, (size_t)k * 4));
+  in_update_B = true;
+  return SC_OK;
+}
+
+int sc_fit::update_B_eval(int t, double* partial_dev) {
+  if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_eval outside update_B_begin/end");
+  if (t < 0 || t >= T) SC_FAIL(ctx, SC_ERR_ARG, "update_B_eval: bad step");
+  // K B is re-evaluated from the current B at every step (cpu.py:486); only this rank's rows are needed here
+  SC_TRY(compute_KB(row_begin, row_end));
+  UpdBArgs g;
+  g.n = n;
+  g.k = k;
+  g.S = S;
+  g.t = t;
+  g.t1 = t1B.p;
+  g.c_ptr = c_ptr.p;
+  g.c_cell = c_cell.p;
+  g.c_t2 = c_t2.p;
+  g.KB = KB.view();
+  g.T2c = T2c.view();
+  g.b_idx = b_idx.p;
+  g.b_val = b_val.p;
+  g.b_cnt = b_cnt.p;
+  g.trace = nullptr;
+  g.evaluated = eval_cnt.p;
+  const long long nchunks = nchunks_cur;
+  pstart();
+  if ((int)ev_a.size() <= t) {
+    cudaEvent_t ea, eb;
+    SC_CUDA(ctx, cudaEventCreate(&ea));
+    SC_CUDA(ctx, cudaEventCreate(&eb));
+    ev_a.push_back(ea);
+    ev_b.push_back(eb);
   }
+  SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
+  if (nchunks > 0) {
+    SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
+    SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
+              bound_v.p);
+    SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
+              part_v.p, part_i.p, bound_v.p);
+  }
+  SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
+  SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p,
+            partial_dev);
+  pstop(P_GEVAL);
+  return SC_OK;
+}
+
+int sc_fit::update_B_step(int t, const double* gathered_dev, int n_ranks, int* trace_dev) {
+  if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_step outside update_B_begin/end");
+  UpdBArgs g;
+  g.n = n;
+  g.k = k;
+  g.S = S;
+  g.t = t;
+  g.t1 = t1B.p;
+  g.c_ptr = c_ptr.p;
+  g.c_cell = c_cell.p;
+  g.c_t2 = c_t2.p;
+  g.KB = KB.view();
+  g.T2c = T2c.view();
+  g.b_idx = b_idx.p;
+  g.b_val = b_val.p;
+  g.b_cnt = b_cnt.p;
+  g.trace = trace_dev;
+  g.evaluated = nullptr;
+  SC_LAUNCH(ctx, k_updateB_step, k, 32, 0, g, gathered_dev, n_ranks);
+  return SC_OK;
+}
+
+int sc_fit::update_B_end() {
+  if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_end without update_B_begin");
+  in_update_B = false;
   {
     unsigned long long ev = 0;
     SC_CUDA(ctx, cudaMemcpyAsync(&ev, eval_cnt.p, sizeof(ev), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1332,13 +1407,31 @@ int sc_fit::update_B(int* trace_dev) {
       eval_ms_total += ms;
       eval_steps++;
     }
-    long long kbn = 0;  // nnz(K B) of the last Frank-Wolfe step
+    long long kbn = 0;  // nnz(K B) of the last Frank-Wolfe step (this rank's rows)
     SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p + 1, 0, sizeof(unsigned long long), ctx->stream));
     SC_LAUNCH(ctx, k_sum_len, (n + 255) / 256, 256, 0, n, KB.len.p, eval_cnt.p + 1);
     SC_CUDA(ctx, cudaMemcpyAsync(&kbn, eval_cnt.p + 1, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     last_kb_nnz = kbn;
   }
+  pre_valid = false;
+  return SC_OK;
+}
+
+// _updateB on one GPU: the split-phase calls back to back (the multi-GPU host inserts one all-gather per step)
+int sc_fit::update_B(int* trace_dev) {
+  SC_TRY(update_B_begin());
+  for (int t = 0; t < T; ++t) {
+    SC_TRY(update_B_eval(t, part_out.p));
+    SC_TRY(update_B_step(t, part_out.p, 1, trace_dev));
+  }
+  return update_B_end();
+}
+
+int sc_fit::set_shard(int r0, int r1) {
+  if (r0 < 0 || r1 > n || r0 > r1) SC_FAIL(ctx, SC_ERR_ARG, "set_shard: bad cell range");
+  row_begin = r0;
+  row_end = r1;
   pre_valid = false;
   return SC_OK;
 }

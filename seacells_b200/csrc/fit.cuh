@@ -8,6 +8,10 @@
 struct sc_fit {
   sc_ctx* ctx = nullptr;
   int n = 0, k = 0, T = 50, S = 50;
+  int row_begin = 0, row_end = 0;  // cells owned by this rank (whole range on one GPU)
+  long long nchunks_cur = 0;
+  bool in_update_B = false;
+  DBuf<double> part_out;  // [k][4] per-archetype partial result of one Frank-Wolfe step of _updateB on this rank
   // kernel matrix M
   DBuf<int> m_ptr, m_col;
   DBuf<double> m_val;
@@ -74,7 +78,12 @@ struct sc_fit {
   int set_A_lists(const long long* colptr, const int* idx, const double* val);
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
-  int compute_KB();
+  int compute_KB(int r0, int r1);
+  int set_shard(int r0, int r1);
+  int update_B_begin();
+  int update_B_eval(int t, double* partial_dev);
+  int update_B_step(int t, const double* gathered_dev, int n_ranks, int* trace_dev);
+  int update_B_end();
   int precompute_A();
   int update_A(double l2, int* trace_dev);
   int update_B(int* trace_dev);

@@ -394,7 +394,7 @@ int sc_fit_stats(sc_fit* fit, long long* out4) {
   out4[7] = fit->last_kb_nnz;
   out4[0] = fit->last_slow_cells;
   out4[1] = fit->last_t2_nnz;
-  out4[2] = fit->last_hubs;
+  out4[2] = fit->last_hub_block;
   out4[3] = fit->sp.last_big_rows;
   return SC_OK;
 }

@@ -537,11 +537,152 @@ struct UpdBArgs {
 };
 
 constexpr int UPB_CHUNK = 1024;  // candidates per CTA
+__device__ __forceinline__ void block_argmin_256(double& v, int& i, double* sg, int* si);
 
-__global__ void k_chunk_count(int k, const long long* __restrict__ c_ptr, int* __restrict__ nch) {
+__global__ void k_chunk_count(int k, const long long* __restrict__ c_ptr, const int* __restrict__ hub_slot,
+                              int* __restrict__ nch) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a > k) return;
-  nch[a] = (a < k) ? (int)((c_ptr[a + 1] - c_ptr[a] + UPB_CHUNK - 1) / UPB_CHUNK) : 0;
+  nch[a] = (a < k && hub_slot[a] < 0) ? (int)((c_ptr[a + 1] - c_ptr[a] + UPB_CHUNK - 1) / UPB_CHUNK) : 0;
+}
+
+// ---- hub block ------------------------------------------------------------------------------------------------------
+// Archetypes for which (almost) every cell is a candidate are evaluated cell-major instead: one pass over the K B rows,
+// each entry (l, v) adding v * t1[l, hubs] to a register tile of all hub columns at once (coalesced 8-byte lanes over
+// the hub index), i.e. a CSR x dense product with the n_hub-wide slice of t1.  Same summation order per (cell, hub) as
+// the candidate path (entries of the K B row in key order), so the gradients are bitwise the same numbers.
+constexpr int HUB_MAX = 128;
+constexpr int HUB_CELLS_PER_CTA = 256;
+
+__global__ void k_hub_t1(int k, int nh, int nh_pad, const int* __restrict__ hub_ids, const double* __restrict__ t1,
+                         double* __restrict__ T1H) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (l >= k) return;
+  T1H[(size_t)l * nh_pad + s] = (s < nh) ? t1[(size_t)hub_ids[s] * k + l] : 0.0;
+}
+__global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restrict__ hub_ids,
+                         const long long* __restrict__ c_ptr, const int* __restrict__ c_cell,
+                         const double* __restrict__ c_t2, double* __restrict__ T2H) {
+  const int s = blockIdx.y;
+  const int a = hub_ids[s];
+  for (long long e = c_ptr[a] + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < c_ptr[a + 1];
+       e += (long long)gridDim.x * blockDim.x)
+    T2H[(size_t)(c_cell[e] - row_begin) * nh_pad + s] = c_t2[e];
+}
+
+// out[cta][slot][4] = {candidate min G, cell, non-candidate min G, cell} over the CTA's cells
+__global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end, int nh_pad, RowLists KB,
+                                                     const double* __restrict__ T1H, const double* __restrict__ T2H,
+                                                     double* __restrict__ out) {
+  __shared__ double s_v[8][2][HUB_MAX];
+  __shared__ int s_i[8][2][HUB_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = nh_pad >> 5;
+  double cv[4], nv[4];
+  int ci[4], ni[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    cv[r] = nv[r] = FW_INF;
+    ci[r] = ni[r] = 0x7fffffff;
+  }
+  const int c0 = row_begin + blockIdx.x * HUB_CELLS_PER_CTA;
+  const int c1 = min(row_end, c0 + HUB_CELLS_PER_CTA);
+  for (int i = c0 + warp; i < c1; i += 8) {
+    const long long p = KB.ptr[i];
+    const int L = KB.len[i];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int x0 = 0; x0 < L; x0 += 32) {
+      int key = 0;
+      double val = 0.0;
+      if (x0 + lane < L) {
+        key = KB.key[p + x0 + lane];
+        val = KB.val[p + x0 + lane];
+      }
+      const int cnt = min(32, L - x0);
+      for (int e = 0; e < cnt; ++e) {
+        const int l = __shfl_sync(0xffffffffu, key, e);
+        const double v = __shfl_sync(0xffffffffu, val, e);
+        const double* __restrict__ trow = T1H + (size_t)l * nh_pad + lane;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (r < R) acc[r] = fma(v, __ldg(trow + r * 32), acc[r]);
+      }
+    }
+    const double* __restrict__ t2row = T2H + (size_t)(i - row_begin) * nh_pad + lane;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < R) {
+        const double t2v = t2row[r * 32];
+        const double G = 2.0 * (acc[r] - t2v);
+        if (t2v > 0.0) {
+          if (G < cv[r]) {  // cells ascend within a warp: strict '<' keeps the first index
+            cv[r] = G;
+            ci[r] = i;
+          }
+        } else if (G < nv[r]) {
+          nv[r] = G;
+          ni[r] = i;
+        }
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r < R) {
+      s_v[warp][0][r * 32 + lane] = cv[r];
+      s_i[warp][0][r * 32 + lane] = ci[r];
+      s_v[warp][1][r * 32 + lane] = nv[r];
+      s_i[warp][1][r * 32 + lane] = ni[r];
+    }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * nh_pad; t += 256) {
+    const int kind = t / nh_pad, slot = t - kind * nh_pad;
+    double v = s_v[0][kind][slot];
+    int i = s_i[0][kind][slot];
+    for (int w = 1; w < 8; ++w) {
+      const double ov = s_v[w][kind][slot];
+      const int oi = s_i[w][kind][slot];
+      if (ov < v || (ov == v && oi < i)) {
+        v = ov;
+        i = oi;
+      }
+    }
+    double* o = out + ((size_t)blockIdx.x * nh_pad + slot) * 4 + kind * 2;
+    o[0] = v;
+    o[1] = (double)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_updateB_hub_reduce(int nctas, int nh_pad, const int* __restrict__ hub_ids,
+                                                            const double* __restrict__ in, double* __restrict__ partial) {
+  __shared__ double sg[8];
+  __shared__ int si[8];
+  const int slot = blockIdx.x;
+  double res[4];
+  for (int kind = 0; kind < 2; ++kind) {
+    double v = FW_INF;
+    int i = 0x7fffffff;
+    for (int c = threadIdx.x; c < nctas; c += 256) {
+      const double* e = in + ((size_t)c * nh_pad + slot) * 4 + kind * 2;
+      const double ov = e[0];
+      const int oi = (int)e[1];
+      if (ov < v || (ov == v && oi < i)) {
+        v = ov;
+        i = oi;
+      }
+    }
+    block_argmin_256(v, i, sg, si);
+    res[kind * 2] = v;
+    res[kind * 2 + 1] = (double)i;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* o = partial + (size_t)hub_ids[slot] * 4;
+    o[0] = res[0];
+    o[1] = res[1];
+    o[2] = res[2];
+    o[3] = res[3];
+  }
 }
 __global__ void k_chunk_fill(int k, const long long* __restrict__ chunk_ptr, int* __restrict__ chunk_arch) {
   const int a = blockIdx.x;
@@ -733,12 +874,14 @@ __global__ void __launch_bounds__(256) k_updateB_local(UpdBArgs g, int row_begin
                                                        const long long* __restrict__ chunk_ptr,
                                                        const double* __restrict__ part_v,
                                                        const int* __restrict__ part_i,
-                                                       const double* __restrict__ bound_v, double* __restrict__ out) {
+                                                       const double* __restrict__ bound_v,
+                                                       const int* __restrict__ hub_slot, double* __restrict__ out) {
   __shared__ double sg[8];
   __shared__ int si[8];
   __shared__ int s_zero;
   const int a = blockIdx.x;
   const int k = g.k;
+  if (hub_slot[a] >= 0) return;  // evaluated cell-major by k_updateB_hub
   const double* __restrict__ row = g.t1 + (size_t)a * k;
   double bv = FW_INF;
   int bi = 0x7fffffff;
@@ -1303,9 +1446,45 @@ int sc_fit::update_B_begin() {
     SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
               c_t2.p);
   }
-  // chunk table: hub archetypes are spread over many CTAs
+  // hub block: archetypes whose candidate list covers more than a quarter of this rank's cells (at most HUB_MAX)
+  {
+    const int nloc = row_end - row_begin;
+    std::vector<long long> hc((size_t)k + 1);
+    SC_CUDA(ctx, cudaMemcpyAsync(hc.data(), c_ptr.p, sizeof(long long) * ((size_t)k + 1), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<long long, int>> big;
+    const long long thr = std::max<long long>(4096, nloc / 4);
+    for (int a = 0; a < k; ++a)
+      if (hc[a + 1] - hc[a] > thr) big.push_back({-(hc[a + 1] - hc[a]), a});
+    std::sort(big.begin(), big.end());
+    if ((int)big.size() > HUB_MAX) big.resize(HUB_MAX);
+    std::vector<int> ids, slot(k, -1);
+    for (auto& b : big) ids.push_back(b.second);
+    std::sort(ids.begin(), ids.end());
+    for (size_t q = 0; q < ids.size(); ++q) slot[ids[q]] = (int)q;
+    n_hub = (int)ids.size();
+    n_hub_pad = ((n_hub + 31) / 32) * 32;
+    SC_TRY(hub_ids.ensure(ctx, (size_t)HUB_MAX));
+    SC_TRY(hub_slot.ensure(ctx, (size_t)k));
+    if (n_hub) SC_CUDA(ctx, cudaMemcpyAsync(hub_ids.p, ids.data(), sizeof(int) * n_hub, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyAsync(hub_slot.p, slot.data(), sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_hub) {
+      const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
+      SC_TRY(T1H.ensure(ctx, (size_t)k * n_hub_pad));
+      SC_TRY(T2H.ensure(ctx, (size_t)nloc * n_hub_pad));
+      SC_TRY(hub_part.ensure(ctx, (size_t)nctas * n_hub_pad * 4));
+      SC_LAUNCH(ctx, k_hub_t1, dim3((k + 255) / 256, n_hub_pad), 256, 0, k, n_hub, n_hub_pad, hub_ids.p, t1B.p, T1H.p);
+      SC_CUDA(ctx, cudaMemsetAsync(T2H.p, 0, sizeof(double) * (size_t)nloc * n_hub_pad, ctx->stream));
+      SC_LAUNCH(ctx, k_hub_t2, dim3(296, n_hub), 256, 0, n_hub, n_hub_pad, row_begin, hub_ids.p, c_ptr.p, c_cell.p,
+                c_t2.p, T2H.p);
+    }
+    last_hub_block = n_hub;
+  }
+  // chunk table: archetypes with long candidate lists are spread over many CTAs
   SC_TRY(chunk_ptr.ensure(ctx, (size_t)k + 1));
-  SC_LAUNCH(ctx, k_chunk_count, (k + 256) / 256, 256, 0, k, c_ptr.p, cnt_k.p);
+  SC_LAUNCH(ctx, k_chunk_count, (k + 256) / 256, 256, 0, k, c_ptr.p, hub_slot.p, cnt_k.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_k.p, chunk_ptr.p, (size_t)k + 1, tmp));
   long long nchunks = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&nchunks, chunk_ptr.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1364,9 +1543,15 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
               part_v.p, part_i.p, bound_v.p);
   }
+  if (n_hub > 0) {
+    const int nloc = row_end - row_begin;
+    const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
+    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, KB.view(), T1H.p, T2H.p, hub_part.p);
+    SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
+  }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
   SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p,
-            partial_dev);
+            hub_slot.p, partial_dev);
   pstop(P_GEVAL);
   return SC_OK;
 }

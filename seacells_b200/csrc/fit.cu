@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end,
         val = KB.val[p + x0 + lane];
       }
       const int cnt = min(32, L - x0);
+#pragma unroll 4
       for (int e = 0; e < cnt; ++e) {
         const int l = __shfl_sync(0xffffffffu, key, e);
         const double v = __shfl_sync(0xffffffffu, val, e);
@@ -744,11 +745,12 @@ __global__ void k_row_max(int rows, RowLists L, double* __restrict__ mv, int* __
 // give two exact lower bounds on the computed G[i,a]:
 //     G >= -2 t2[i,a]                                   (the product term is >= 0)
 //     G >= 2 (fl(KBmax_i * t1[lmax_i, a]) - t2[i,a])    (a sum of non-negative terms is >= any one of them)
-// so once a first pass over the 256 largest-t2 candidates has produced a minimum `bound`, any candidate whose lower
+// so once a first pass over the UPB_R0 largest-t2 candidates has produced a minimum `bound`, any candidate whose lower
 // bound exceeds it can neither be the argmin nor tie with it and is skipped without reading its K B row.  This is what
-// keeps "hub" archetypes (every cell is a candidate) affordable.  round 0 = first 256 candidates of every archetype,
+// keeps long candidate lists affordable.  round 0 = first UPB_R0 candidates of every archetype,
 // round 1 = everything else.
 constexpr int UPB_LONG = 192;
+constexpr int UPB_R0 = 64;  // candidates evaluated unconditionally to seed the bound
 __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, const long long* __restrict__ chunk_ptr,
                                                       const int* __restrict__ chunk_arch,
                                                       const double* __restrict__ cmax_v, const int* __restrict__ cmax_l,
@@ -770,8 +772,8 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   const long long c0 = g.c_ptr[a] + (long long)chunk * UPB_CHUNK;
   const int nc = (int)min((long long)UPB_CHUNK, g.c_ptr[a + 1] - c0);
   const double bound = (round == 0) ? FW_INF : bound_v[a];
-  const int e_begin = (round == 1 && chunk == 0) ? 256 : 0;
-  const int e_end = (round == 0) ? min(nc, 256) : nc;
+  const int e_begin = (round == 1 && chunk == 0) ? UPB_R0 : 0;
+  const int e_end = (round == 0) ? min(nc, UPB_R0) : nc;
   // phase 1: cheap bound tests, survivors compacted into shared memory
   __shared__ int q_cell[UPB_CHUNK];
   __shared__ double q_t2[UPB_CHUNK];
@@ -1257,7 +1259,7 @@ RowLists sc_fit::A_view() const {
 }
 
 // KB rows and t1A for the current B (shared by _updateA and compute_RSS)
-int sc_fit::compute_KB(int r0, int r1) {
+int sc_fit::compute_KB(int r0, int r1, bool sorted) {
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   // B by cell
   pstart();
@@ -1286,10 +1288,10 @@ int sc_fit::compute_KB(int r0, int r1) {
   RowLists Bl = brow.view();
   pstop(P_BROW);
   pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, k, Y, sp));
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, k, Y, sp, sorted));
   pstop(P_SPGEMM_Y);
   pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, r0, r1, Y.view(), k, KB, sp));
+  SC_TRY(sc_spgemm_rows(ctx, M, r0, r1, Y.view(), k, KB, sp, sorted));
   pstop(P_SPGEMM_KB);
   return SC_OK;
 }
@@ -1297,7 +1299,7 @@ int sc_fit::compute_KB(int r0, int r1) {
 int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
-  SC_TRY(compute_KB(0, n));  // all rows: t1 and the RSS need K B at every cell (replicated across ranks)
+  SC_TRY(compute_KB(0, n, true));  // all rows, key-sorted (lookups): t1 and the RSS need K B at every cell (replicated across ranks)
   pstart();
   SC_CUDA(ctx, cudaMemsetAsync(t1A.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
   SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p, KB.view(), t1A.p);
@@ -1509,7 +1511,7 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_eval outside update_B_begin/end");
   if (t < 0 || t >= T) SC_FAIL(ctx, SC_ERR_ARG, "update_B_eval: bad step");
   // K B is re-evaluated from the current B at every step (cpu.py:486); only this rank's rows are needed here
-  SC_TRY(compute_KB(row_begin, row_end));
+  SC_TRY(compute_KB(row_begin, row_end, false));  // rows are only walked here: first-occurrence order
   UpdBArgs g;
   g.n = n;
   g.k = k;

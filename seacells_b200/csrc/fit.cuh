@@ -81,7 +81,7 @@ struct sc_fit {
   int set_A_lists(const long long* colptr, const int* idx, const double* val);
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
-  int compute_KB(int r0, int r1);
+  int compute_KB(int r0, int r1, bool sorted);
   int set_shard(int r0, int r1);
   int update_B_begin();
   int update_B_eval(int t, double* partial_dev);

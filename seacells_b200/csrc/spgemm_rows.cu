@@ -182,6 +182,136 @@ k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const i
   }
 }
 
+// First-occurrence variant used inside the Frank-Wolfe loop of _updateB, where the consumers only walk the rows: keys
+// are appended in the order they first appear in the (row of S, row of X) sequence - a fixed order - so neither the
+// compaction nor the sort is needed.  The table maps key -> list index; one leader lane per distinct key of a batch does
+// the find-or-insert, new indices are handed out in lane order, duplicates are accumulated rank by rank as above.
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_spgemm_fill_fo(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
+                 const double* __restrict__ s_val, RowLists X, const long long* __restrict__ z_ptr,
+                 int* __restrict__ z_len, int* __restrict__ z_key, double* __restrict__ z_val, int* __restrict__ flags,
+                 int* __restrict__ big_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* lvals = reinterpret_cast<double*>(smem_raw) + (size_t)warp * CAP;
+  int* tkeys = reinterpret_cast<int*>(smem_raw + (size_t)WARPS * CAP * sizeof(double)) + (size_t)warp * CAP;
+  unsigned short* tidx = reinterpret_cast<unsigned short*>(smem_raw + (size_t)WARPS * CAP * (sizeof(double) + sizeof(int))) +
+                         (size_t)warp * CAP;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int i = row_begin + blockIdx.x * WARPS + warp; i < row_end; i += gridDim.x * WARPS) {
+    const long long zp = z_ptr[i];
+    const long long ub = z_ptr[i + 1] - zp;
+    if (ub == 0) {
+      if (lane == 0) z_len[i] = 0;
+      continue;
+    }
+    int cap = 64;
+    while (cap < CAP && (long long)cap * 4 < 5 * ub) cap <<= 1;  // load factor <= 0.8 even if every key is distinct
+    const int capm = cap - 1;
+    const int limit = min((long long)(CAP - (CAP >> 3)), ub);
+    for (int t = lane; t < cap; t += 32) tkeys[t] = -1;
+    __syncwarp();
+    int uniq = 0;
+    bool overflow = false;
+    const int s0 = s_ptr[i], s1 = s_ptr[i + 1];
+    for (int base = s0; base < s1 && !overflow; base += 32) {
+      int q = -1, xl = 0;
+      double m = 0.0;
+      long long xp = 0;
+      if (base + lane < s1) {
+        q = s_col[base + lane];
+        m = s_val[base + lane];
+        xl = X.len[q];
+        xp = X.ptr[q];
+      }
+      int incl = xl;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int tot = __shfl_sync(FULL, incl, 31);
+      for (int f0 = 0; f0 < tot; f0 += 32) {
+        const int f = f0 + lane;
+        const bool valid = f < tot;
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          int pv = __shfl_sync(FULL, incl, lo + step - 1);
+          if (pv <= f) lo += step;
+        }
+        lo = min(lo, 31);
+        const int o_incl = __shfl_sync(FULL, incl, lo);
+        const int o_len = __shfl_sync(FULL, xl, lo);
+        const long long o_ptr = __shfl_sync(FULL, xp, lo);
+        const double o_m = __shfl_sync(FULL, m, lo);
+        int key = -1 - lane;
+        double c = 0.0;
+        if (valid) {
+          const long long e = o_ptr + (f - (o_incl - o_len));
+          key = X.key[e];
+          c = __dmul_rn(o_m, X.val[e]);
+        }
+        const unsigned kgrp = __match_any_sync(FULL, key);
+        const int leader = __ffs(kgrp) - 1;
+        bool is_new = false;
+        int slot = 0, idx = 0;
+        if (valid && lane == leader) {
+          int s = hash_key(key) & capm;
+          while (true) {
+            const int prev = atomicCAS(&tkeys[s], -1, key);
+            if (prev == -1) {
+              is_new = true;
+              break;
+            }
+            if (prev == key) break;
+            s = (s + 1) & capm;
+          }
+          slot = s;
+        }
+        const unsigned newmask = __ballot_sync(FULL, is_new);
+        if (uniq + __popc(newmask) > limit) {
+          overflow = true;
+          break;
+        }
+        if (valid && lane == leader) {
+          if (is_new) {
+            idx = uniq + __popc(newmask & lt_mask);
+            tidx[slot] = (unsigned short)idx;
+            lvals[idx] = 0.0;
+            z_key[zp + idx] = key;
+          } else {
+            idx = tidx[slot];
+          }
+        }
+        uniq += __popc(newmask);
+        __syncwarp();
+        const int myidx = __shfl_sync(FULL, idx, leader);
+        const int rank = __popc(kgrp & lt_mask);
+        const int maxcnt = __reduce_max_sync(FULL, valid ? __popc(kgrp) : 0);
+        for (int r = 0; r < maxcnt; ++r) {
+          if (valid && rank == r) lvals[myidx] = __dadd_rn(lvals[myidx], c);
+          __syncwarp();
+        }
+      }
+    }
+    if (overflow) {
+      if (lane == 0) {
+        big_list[atomicAdd(&flags[0], 1)] = i;
+        z_len[i] = 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    if (lane == 0) z_len[i] = uniq;
+    for (int t = lane; t < uniq; t += 32) z_val[zp + t] = lvals[t];
+    __syncwarp();
+  }
+}
+
 // Rows with more distinct keys than the shared-memory table holds (cells next to a "hub" cell that many archetypes
 // put weight on - a by-product of the reference's argmin-of-zeros rule): one CTA per row, dense accumulator over the
 // whole key space in global scratch.  Keys of one X row are distinct, X rows are applied one after the other, so the
@@ -242,7 +372,7 @@ k_spgemm_big(int nbig, const int* __restrict__ big_list, int key_space, const in
 }
 
 int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
-                   RowListsBuf& Z, SpgemmScratch& sc) {
+                   RowListsBuf& Z, SpgemmScratch& sc, bool sorted) {
   constexpr int CAP = 512, WARPS = 8;
   const int n = S.n;
   SC_TRY(sc.ub.ensure(ctx, (size_t)n + 1));
@@ -269,8 +399,20 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
     attr_set = true;
   }
   int grid = std::min((rows + WARPS - 1) / WARPS, 148 * 16);
-  SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
-            X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+  if (sorted) {
+    SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
+              X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+  } else {
+    const size_t smem_fo = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int) + sizeof(unsigned short));
+    static bool attr_fo = false;
+    if (!attr_fo) {
+      SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill_fo<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_fo));
+      attr_fo = true;
+    }
+    SC_LAUNCH(ctx, (k_spgemm_fill_fo<CAP, WARPS>), grid, WARPS * 32, smem_fo, row_begin, row_end, S.indptr, S.indices,
+              S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+  }
   int nbig = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&nbig, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -10,6 +10,6 @@ struct SpgemmScratch {
 };
 
 // Z[i,:] = sum_q S[i,q] * X[q,:] for rows i in [row_begin,row_end); other rows of Z are empty.  Rows sorted by key.
-// key_space: keys of X are in [0, key_space).
+// key_space: keys of X are in [0, key_space).  sorted = false: rows come out in first-occurrence order (fixed, cheaper).
 int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
-                   RowListsBuf& Z, SpgemmScratch& sc);
+                   RowListsBuf& Z, SpgemmScratch& sc, bool sorted = true);

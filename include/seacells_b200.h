@@ -48,6 +48,11 @@ const char* sc_version(void);
  * idx_out / d2_out: [(row_end-row_begin) x (n_neighbors-1)], neighbours by (squared distance, index), self excluded. */
 int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int row_begin, int row_end,
            int32_t* idx_out, double* d2_out);
+/* For n >= 2048 sc_knn shortlists 32 candidates per query with an fp32 distance tile kernel and re-ranks them with the
+ * exact fp64 distance; a per-query certificate proves that nothing was missed, otherwise the query is recomputed by the
+ * all-fp64 kernel (results are bit-identical either way; SC_KNN_EXACT=1 in the environment forces the all-fp64 kernel).
+ * Number of queries of the last call that needed the recomputation: */
+int sc_knn_fallback_rows(sc_ctx* ctx);
 
 /* SEACellGraph.rbf(k, graph_construction) (build_graph.py:113): kNN, sigma (18-34), union/intersection (155-164),
  * Gaussian values (37-61), CSR (181-188).  intersection: 0 = "union", 1 = "intersect"/"intersection". */

@@ -109,6 +109,7 @@ void sc_ctx_destroy(sc_ctx* ctx) {
 
 const char* sc_last_error(sc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 unsigned long long sc_launch_count(sc_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+int sc_knn_fallback_rows(sc_ctx* ctx) { return ctx ? ctx->last_knn_fallback : 0; }
 void* sc_stream(sc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int sc_sync(sc_ctx* ctx) {

@@ -28,6 +28,7 @@ struct sc_ctx {
   void* nccl = nullptr;  // ncclComm_t when world > 1
   // launch counter: every kernel launched by the library goes through SC_LAUNCH and bumps this
   unsigned long long launches = 0;
+  int last_knn_fallback = 0;  // queries of the last kNN call that failed the filter certificate (recomputed exactly)
 };
 
 #define SC_CUDA(ctx, call)                                                                  \

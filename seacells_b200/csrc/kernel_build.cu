@@ -10,6 +10,7 @@
 #include "kernel_build.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 constexpr int KNN_QT = 64;   // queries per CTA
 constexpr int KNN_RT = 64;   // references per tile
@@ -19,8 +20,9 @@ constexpr int KNN_QPW = KNN_QT / (KNN_THREADS / 32);  // queries per warp in the
 
 template <typename TX>
 __global__ void __launch_bounds__(KNN_THREADS)
-k_knn_exact(const TX* __restrict__ X, int n, int d, int kk, int row_begin, int row_end, int* __restrict__ out_idx,
-            double* __restrict__ out_d2) {
+k_knn_exact(const TX* __restrict__ X, int n, int d, int kk, int row_begin, int row_end,
+            const int* __restrict__ row_list, int out_base, int* __restrict__ out_idx, double* __restrict__ out_d2) {
+  // queries are positions [row_begin,row_end); with a row_list they are row_list[pos] (fallback rows of the filter path)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TX* sq = reinterpret_cast<TX*>(smem_raw);                    // [KNN_DC][KNN_QT]
   TX* sr = sq + KNN_DC * KNN_QT;                                // [KNN_DC][KNN_RT]
@@ -43,8 +45,9 @@ k_knn_exact(const TX* __restrict__ X, int n, int d, int kk, int row_begin, int r
     const int dc = min(KNN_DC, d - c0);
     for (int e = tid; e < KNN_QT * dc; e += KNN_THREADS) {
       const int qq = e / dc, c = e - qq * dc;
-      const int gq = q0 + qq;
-      sq[c * KNN_QT + qq] = (gq < row_end) ? X[(size_t)gq * d + c0 + c] : (TX)0;
+      const int pq = q0 + qq;
+      const int gq = (pq < row_end) ? (row_list ? row_list[pq] : pq) : 0;
+      sq[c * KNN_QT + qq] = (pq < row_end) ? X[(size_t)gq * d + c0 + c] : (TX)0;
     }
   };
   if (single_chunk) load_q(0);
@@ -89,8 +92,9 @@ k_knn_exact(const TX* __restrict__ X, int n, int d, int kk, int row_begin, int r
 #pragma unroll
     for (int q = 0; q < KNN_QPW; ++q) {
       const int qq = warp * KNN_QPW + q;
-      const int gq = q0 + qq;
-      if (gq >= row_end) continue;
+      const int pq = q0 + qq;
+      if (pq >= row_end) continue;
+      const int gq = row_list ? row_list[pq] : pq;
 #pragma unroll
       for (int h = 0; h < KNN_RT / 32; ++h) {
         const int rr = h * 32 + lane;
@@ -124,23 +128,236 @@ k_knn_exact(const TX* __restrict__ X, int n, int d, int kk, int row_begin, int r
   }
 #pragma unroll
   for (int q = 0; q < KNN_QPW; ++q) {
-    const int gq = q0 + warp * KNN_QPW + q;
-    if (gq < row_end && lane < kk) {
-      out_idx[(size_t)(gq - row_begin) * kk + lane] = li[q];
-      out_d2[(size_t)(gq - row_begin) * kk + lane] = ld[q];
+    const int pq = q0 + warp * KNN_QPW + q;
+    if (pq < row_end && lane < kk) {
+      const int gq = row_list ? row_list[pq] : pq;
+      out_idx[(size_t)(gq - out_base) * kk + lane] = li[q];
+      out_d2[(size_t)(gq - out_base) * kk + lane] = ld[q];
     }
   }
 }
 
 template <typename TX>
-static int launch_knn(sc_ctx* ctx, const TX* X, int n, int d, int kk, int row_begin, int row_end, int* idx, double* d2) {
+static int launch_knn(sc_ctx* ctx, const TX* X, int n, int d, int kk, int row_begin, int row_end, const int* row_list,
+                      int out_base, int* idx, double* d2) {
   const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(TX) + (size_t)KNN_QT * (KNN_RT + 1) * sizeof(double);
   SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_exact<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int rows = row_end - row_begin;
   if (rows <= 0) return SC_OK;
-  SC_LAUNCH(ctx, k_knn_exact<TX>, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, X, n, d, kk, row_begin, row_end, idx,
-            d2);
+  SC_LAUNCH(ctx, k_knn_exact<TX>, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, X, n, d, kk, row_begin, row_end,
+            row_list, out_base, idx, d2);
   return SC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 filter + exact re-rank
+// Stage 1: approximate squared distances ||xi||^2 + ||xj||^2 - 2 xi.xj on the mean-centred embedding in fp32 (FFMA
+//          tiles), fused warp-level top-32 per query.
+// Stage 2: the 32 survivors are re-ranked with the exact fp64 difference-form distance (same operation sequence as
+//          k_knn_exact), sorted by (d2, index), the best n_neighbors-1 kept.
+// Certificate: every excluded j has approx(i,j) >= thr_i (the 32nd approximate distance) and |approx - exact| <= eps_i,
+//          so exact(i,j) >= thr_i - eps_i; if the exact (n_neighbors-1)-th distance is < thr_i - eps_i no excluded point
+//          can belong to (or tie with) the result.  Queries that fail the certificate are recomputed by k_knn_exact.
+//          The result is therefore bit-identical to the exact kernel's.
+constexpr int KF_NC = 32;
+
+__global__ void k_col_mean(const void* __restrict__ X, int x_is_f64, int n, int d, double* __restrict__ mean) {
+  __shared__ double sh[256];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256)
+    acc += x_is_f64 ? ((const double*)X)[(size_t)i * d + c] : (double)((const float*)X)[(size_t)i * d + c];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[c] = sh[0] / (double)n;
+}
+
+__global__ void k_center(const void* __restrict__ X, int x_is_f64, int n, int d, const double* __restrict__ mean,
+                         float* __restrict__ Xc, float* __restrict__ norm2, float* __restrict__ maxnorm_bits) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  float acc = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const double x = x_is_f64 ? ((const double*)X)[(size_t)warp * d + c] : (double)((const float*)X)[(size_t)warp * d + c];
+    const float v = (float)(x - mean[c]);
+    Xc[(size_t)warp * d + c] = v;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    norm2[warp] = acc;
+    atomicMax(reinterpret_cast<int*>(maxnorm_bits), __float_as_int(acc));  // acc >= 0: int order == float order
+  }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn_filter(const float* __restrict__ Xc, const float* __restrict__ norm2, int n, int d, int row_begin, int row_end,
+             int* __restrict__ cand_idx, float* __restrict__ cand_thr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);   // [KNN_DC][KNN_QT]
+  float* sr = sq + KNN_DC * KNN_QT;                   // [KNN_DC][KNN_RT]
+  float* sd = sr + KNN_DC * KNN_RT;                   // [KNN_QT][KNN_RT + 1]
+  float* snr = sd + KNN_QT * (KNN_RT + 1);            // [KNN_RT] reference norms
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int q0 = row_begin + blockIdx.x * KNN_QT;
+  const bool single_chunk = d <= KNN_DC;
+  float ld[KNN_QPW];
+  int li[KNN_QPW];
+#pragma unroll
+  for (int q = 0; q < KNN_QPW; ++q) {
+    ld[q] = INFINITY;
+    li[q] = 0x7fffffff;
+  }
+  float qn[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gq = q0 + ty * 4 + a;
+    qn[a] = gq < row_end ? norm2[gq] : 0.f;
+  }
+  auto load_q = [&](int c0) {
+    const int dc = min(KNN_DC, d - c0);
+    const int qq = tid & (KNN_QT - 1);
+    const int gq = q0 + qq;
+    const float* __restrict__ src = Xc + (size_t)min(gq, n - 1) * d + c0;
+    for (int c = tid >> 6; c < dc; c += KNN_THREADS / KNN_QT) sq[c * KNN_QT + qq] = (gq < row_end) ? src[c] : 0.f;
+  };
+  if (single_chunk) load_q(0);
+  for (int r0 = 0; r0 < n; r0 += KNN_RT) {
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int c0 = 0; c0 < d; c0 += KNN_DC) {
+      const int dc = min(KNN_DC, d - c0);
+      __syncthreads();
+      if (!single_chunk) load_q(c0);
+      {
+        const int rr = tid & (KNN_RT - 1);
+        const int gr = r0 + rr;
+        const float* __restrict__ src = Xc + (size_t)min(gr, n - 1) * d + c0;
+        for (int c = tid >> 6; c < dc; c += KNN_THREADS / KNN_RT) sr[c * KNN_RT + rr] = (gr < n) ? src[c] : 0.f;
+      }
+      if (c0 == 0 && tid < KNN_RT) snr[tid] = (r0 + tid < n) ? norm2[r0 + tid] : 0.f;
+      __syncthreads();
+#pragma unroll 2
+      for (int c = 0; c < dc; ++c) {
+        const float4 qv = *reinterpret_cast<const float4*>(sq + c * KNN_QT + ty * 4);
+        const float4 rv = *reinterpret_cast<const float4*>(sr + c * KNN_RT + tx * 4);
+        const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ra[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(qa[a], ra[b], acc[a][b]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        sd[(ty * 4 + a) * (KNN_RT + 1) + tx * 4 + b] = fmaf(-2.f, acc[a][b], qn[a] + snr[tx * 4 + b]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KNN_QPW; ++q) {
+      const int qq = warp * KNN_QPW + q;
+      const int gq = q0 + qq;
+      if (gq >= row_end) continue;
+#pragma unroll
+      for (int h = 0; h < KNN_RT / 32; ++h) {
+        const int rr = h * 32 + lane;
+        const int gr = r0 + rr;
+        const float dv = sd[qq * (KNN_RT + 1) + rr];
+        const float td = __shfl_sync(0xffffffffu, ld[q], KF_NC - 1);
+        const bool cand = gr < n && gr != gq && dv < td;
+        unsigned ball = __ballot_sync(0xffffffffu, cand);
+        while (ball) {
+          const int src = __ffs(ball) - 1;
+          ball &= ball - 1;
+          const float cd = __shfl_sync(0xffffffffu, dv, src);
+          const int ci = __shfl_sync(0xffffffffu, gr, src);
+          const bool less = ld[q] <= cd;  // ties keep the earlier reference; any fixed rule works for a filter
+          const int p = __popc(__ballot_sync(0xffffffffu, less));
+          const float ud = __shfl_up_sync(0xffffffffu, ld[q], 1);
+          const int ui = __shfl_up_sync(0xffffffffu, li[q], 1);
+          if (p < KF_NC) {
+            if (lane == p) {
+              ld[q] = cd;
+              li[q] = ci;
+            } else if (lane > p) {
+              ld[q] = ud;
+              li[q] = ui;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KNN_QPW; ++q) {
+    const int gq = q0 + warp * KNN_QPW + q;
+    if (gq < row_end) {
+      cand_idx[(size_t)(gq - row_begin) * KF_NC + lane] = li[q];
+      if (lane == KF_NC - 1) cand_thr[gq - row_begin] = ld[q];
+    }
+  }
+}
+
+template <typename TX>
+__global__ void k_knn_rerank(const TX* __restrict__ X, const float* __restrict__ norm2, const float* __restrict__ maxnorm,
+                             int n, int d, int kk, int row_begin, int row_end, const int* __restrict__ cand_idx,
+                             const float* __restrict__ cand_thr, double gamma, int* __restrict__ out_idx,
+                             double* __restrict__ out_d2, int* __restrict__ fail_list, int* __restrict__ fail_cnt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int gq = row_begin + warp;
+  if (gq >= row_end) return;
+  int j = cand_idx[(size_t)warp * KF_NC + lane];
+  double dd = INFINITY;
+  if (j != 0x7fffffff) {
+    const TX* __restrict__ xi = X + (size_t)gq * d;
+    const TX* __restrict__ xj = X + (size_t)j * d;
+    double acc = 0.0;
+    for (int c = 0; c < d; ++c) {
+      const double df = __dsub_rn((double)xi[c], (double)xj[c]);
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+    }
+    dd = acc;
+  }
+  // bitonic sort of the 32 (d2, index) pairs across the warp, ascending
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int st = k2 >> 1; st > 0; st >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, dd, st);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, st);
+      const bool up = (lane & k2) == 0;
+      const bool lower = (lane & st) == 0;
+      const bool mine_less = dd < od || (dd == od && j < oj);
+      const bool keep_mine = (lower == up) ? mine_less : !mine_less;
+      if (!keep_mine) {
+        dd = od;
+        j = oj;
+      }
+    }
+  }
+  // certificate
+  const double dk = __shfl_sync(0xffffffffu, dd, kk - 1);
+  const double nq = (double)norm2[gq], nm = (double)maxnorm[0];
+  const double eps = gamma * (nq + nm + 2.0 * sqrt(nq * nm));
+  const double thr = (double)cand_thr[warp];
+  const bool ok = dk < thr - eps;  // false for NaN / inf as well
+  if (!ok) {
+    if (lane == 0) fail_list[atomicAdd(fail_cnt, 1)] = gq;
+    return;
+  }
+  if (lane < kk) {
+    out_idx[(size_t)warp * kk + lane] = j;
+    out_d2[(size_t)warp * kk + lane] = dd;
+  }
 }
 
 int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int row_begin,
@@ -149,8 +366,52 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
   if (kk < 1 || kk > 32) SC_FAIL(ctx, SC_ERR_ARG, "knn: n_neighbors must be in [2, 33]");
   if (n <= kk) SC_FAIL(ctx, SC_ERR_ARG, "knn: need more cells than neighbours");
   if (row_begin < 0 || row_end > n || row_begin > row_end) SC_FAIL(ctx, SC_ERR_ARG, "knn: bad row range");
-  if (x_is_f64) return launch_knn<double>(ctx, (const double*)X, n, d, kk, row_begin, row_end, idx, d2);
-  return launch_knn<float>(ctx, (const float*)X, n, d, kk, row_begin, row_end, idx, d2);
+  const int rows = row_end - row_begin;
+  if (rows == 0) return SC_OK;
+  const bool use_filter = n >= 2048 && kk <= 24 && n > KF_NC + 1 && getenv("SC_KNN_EXACT") == nullptr;
+  if (!use_filter) {
+    if (x_is_f64) return launch_knn<double>(ctx, (const double*)X, n, d, kk, row_begin, row_end, nullptr, row_begin, idx, d2);
+    return launch_knn<float>(ctx, (const float*)X, n, d, kk, row_begin, row_end, nullptr, row_begin, idx, d2);
+  }
+  DBuf<double> mean;
+  DBuf<float> Xc, norm2, maxnorm, thr;
+  DBuf<int> cand, fail;
+  SC_TRY(mean.ensure(ctx, (size_t)d));
+  SC_TRY(Xc.ensure(ctx, (size_t)n * d));
+  SC_TRY(norm2.ensure(ctx, (size_t)n));
+  SC_TRY(maxnorm.ensure(ctx, 4));
+  SC_TRY(thr.ensure(ctx, (size_t)rows));
+  SC_TRY(cand.ensure(ctx, (size_t)rows * KF_NC));
+  SC_TRY(fail.ensure(ctx, (size_t)rows + 4));
+  SC_CUDA(ctx, cudaMemsetAsync(maxnorm.p, 0, sizeof(float) * 4, ctx->stream));
+  SC_CUDA(ctx, cudaMemsetAsync(fail.p + rows, 0, sizeof(int) * 4, ctx->stream));
+  SC_LAUNCH(ctx, k_col_mean, d, 256, 0, X, x_is_f64, n, d, mean.p);
+  SC_LAUNCH(ctx, k_center, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, X, x_is_f64, n, d, mean.p, Xc.p, norm2.p,
+            maxnorm.p);
+  const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(float) + (size_t)KNN_QT * (KNN_RT + 1) * sizeof(float) +
+                      KNN_RT * sizeof(float);
+  SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SC_LAUNCH(ctx, k_knn_filter, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, Xc.p, norm2.p, n, d, row_begin, row_end,
+            cand.p, thr.p);
+  // error bound of the fp32 pipeline (conversion, norms, d-term dot product, final combination), 4x conservative
+  const double gamma = (double)(d + 8) * 4.0 * 5.9604644775390625e-08;
+  if (x_is_f64) {
+    SC_LAUNCH(ctx, k_knn_rerank<double>, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, (const double*)X, norm2.p,
+              maxnorm.p, n, d, kk, row_begin, row_end, cand.p, thr.p, gamma, idx, d2, fail.p, fail.p + rows);
+  } else {
+    SC_LAUNCH(ctx, k_knn_rerank<float>, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, (const float*)X, norm2.p,
+              maxnorm.p, n, d, kk, row_begin, row_end, cand.p, thr.p, gamma, idx, d2, fail.p, fail.p + rows);
+  }
+  int nfail = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&nfail, fail.p + rows, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->last_knn_fallback = nfail;
+  if (nfail > 0) {
+    if (x_is_f64) SC_TRY(launch_knn<double>(ctx, (const double*)X, n, d, kk, 0, nfail, fail.p, row_begin, idx, d2));
+    else SC_TRY(launch_knn<float>(ctx, (const float*)X, n, d, kk, 0, nfail, fail.p, row_begin, idx, d2));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SC_OK;
 }
 
 // ---- sigma_i: (kn//2)-th smallest non-zero Euclidean neighbour distance, 0 when there are fewer (np.linalg.norm([]))

@@ -68,6 +68,43 @@ def test_knn_vs_oracle_ragged_and_duplicates():
         np.testing.assert_allclose(M.data, Mo.data, rtol=M_RTOL, atol=0)
 
 
+def test_knn_filter_path_is_exact():
+    """n >= 2048 takes the fp32-filter + fp64 re-rank path: it must return exactly what the all-fp64 kernel returns."""
+    import subprocess
+    import sys
+    from seacells_b200 import _lib, knn
+    from seacells_b200.synth import synth_embedding
+    rng = np.random.default_rng(11)
+    ctx = _lib.default_context()
+    # (a) against the numpy oracle at a size it can still do
+    X = synth_embedding(6000, 50, 3)
+    idx, d2 = knn(X, 15)
+    io, do = O.knn_exact(X, 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    assert ctx.lib.sc_knn_fallback_rows(ctx.h) < 60          # the certificate passes almost everywhere
+    # (b) adversarial: tight clusters far from the origin (cancellation), duplicates, a far outlier, float64 input
+    Xa = (rng.normal(size=(5000, 20)) * 1e-3 + rng.integers(0, 5, size=(5000, 1)) * 50.0 + 1000.0).astype(np.float32)
+    Xa[100:110] = Xa[99]
+    Xa[4999] = 1e4
+    ia, da = knn(Xa, 15)
+    ioa, doa = O.knn_exact(Xa, 15)
+    assert np.array_equal(ia, ioa) and np.array_equal(da, doa)
+    Xd = rng.normal(size=(4000, 33))
+    i64, d64 = knn(Xd, 10)
+    io64, do64 = O.knn_exact(Xd, 10)
+    assert np.array_equal(i64, io64) and np.array_equal(d64, do64)
+    # (c) large: filter path vs the all-fp64 kernel (forced through the environment in a child process)
+    n = 60000
+    Xl = synth_embedding(n, 50, 0)
+    il, dl = knn(Xl, 15)
+    np.save("/tmp/_knn_X.npy", Xl)
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from seacells_b200 import knn; "
+            "X = np.load('/tmp/_knn_X.npy'); i, d = knn(X, 15); np.save('/tmp/_knn_i.npy', i); np.save('/tmp/_knn_d.npy', d)"
+            % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(__import__("os").environ, SC_KNN_EXACT="1"))
+    assert np.array_equal(il, np.load("/tmp/_knn_i.npy")) and np.array_equal(dl, np.load("/tmp/_knn_d.npy"))
+
+
 def test_spmm_csr_dense():
     from seacells_b200 import spmm_csr
     rng = np.random.default_rng(0)

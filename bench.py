@@ -261,7 +261,7 @@ def run_ours(args):
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(n), "cells_per_gpu": n, "outer_iterations": n_iter,
+           "config": {"workload": workload_name(n), "cells_per_gpu": n // world if world > 1 else n, "outer_iterations": n_iter,
                       "converged": bool(conv), "rss_first_last": [rss[0], rss[-1]],
                       "fit_seconds": t_dev / args.steps, "construct_kernel_matrix_s": t_build,
                       "l2_policy": "inputs (>= 1 GB of lists per step) exceed the 126 MB L2; no explicit flush",

@@ -428,13 +428,13 @@ __global__ void k_row_bounds(int k, const unsigned long long* __restrict__ keys,
 // t1B[l][a] = sum_j A[l,j] A[a,j], cells j ascending (the order of scipy's csr_matmat for A @ A.T, cpu.py:480).
 // Rows longer than `hub_thr` cells ("hub" archetypes: low-index archetypes that collect a little weight from almost
 // every cell through the argmin-of-zeros rule) are skipped here and filled by k_gram_mirror / k_gram_hubpair.
-__global__ void k_gram(int k, int S, long long hub_thr, const long long* __restrict__ rptr,
+__global__ void k_gram(int k, int S, const unsigned char* __restrict__ is_hub, const long long* __restrict__ rptr,
                        const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
                        const int* __restrict__ a_idx, const double* __restrict__ a_val,
                        const int* __restrict__ a_cnt, double* __restrict__ t1) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= k) return;
-  if (rptr[warp + 1] - rptr[warp] > hub_thr) return;
+  if (is_hub[warp]) return;
   double* row = t1 + (size_t)warp * k;
   for (long long e = rptr[warp]; e < rptr[warp + 1]; ++e) {
     const int j = (int)(keys[e] & 0xffffffffu);
@@ -455,41 +455,68 @@ __global__ void k_gram_mirror(int k, int nhub, const int* __restrict__ hubs, con
   if (a >= k || is_hub[a]) return;
   t1[(size_t)h * k + a] = t1[(size_t)a * k + h];
 }
-// hub x hub entries: fixed-shape parallel reduction over the cells of the first hub's row
+// hub x hub entries, cell-major: a CTA walks a contiguous block of cells in index order; for each cell the weights it
+// puts on hub archetypes are staged in shared memory and all pairs are added into the CTA's private H x H tile (targets
+// of one cell are distinct, cells are sequential => fixed order).  The per-CTA tiles are then summed in CTA order.
+constexpr int GRAM_HUB_MAX = 160;
+constexpr int GRAM_HUB_CELLS = 4096;
 __global__ void __launch_bounds__(256)
-k_gram_hubpair(int k, int S, int nhub, const int* __restrict__ hubs, const long long* __restrict__ rptr,
-               const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
-               const int* __restrict__ a_idx, const double* __restrict__ a_val, const int* __restrict__ a_cnt,
-               double* __restrict__ t1) {
-  __shared__ double sh[256];
-  // blockIdx.x enumerates pairs (p, q) with p <= q
-  int p = 0, rem = blockIdx.x;
-  while (rem >= nhub - p) {
-    rem -= nhub - p;
-    p++;
-  }
-  const int q = p + rem;
-  const int l = hubs[p], l2 = hubs[q];
-  double acc = 0.0;
-  for (long long e = rptr[l] + threadIdx.x; e < rptr[l + 1]; e += 256) {
-    const int j = (int)(keys[e] & 0xffffffffu);
-    const int cnt = a_cnt[j];
-    for (int s = 0; s < cnt; ++s)
-      if (a_idx[(size_t)j * S + s] == l2) {
-        acc = __dadd_rn(acc, __dmul_rn(vals[e], a_val[(size_t)j * S + s]));
-        break;
+k_gram_hub_tiles(int n, int S, int H, const int* __restrict__ hub_of /* [k] -> hub index or -1 */,
+                 const int* __restrict__ a_idx, const double* __restrict__ a_val, const int* __restrict__ a_cnt,
+                 double* __restrict__ tiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);            // [H*H]
+  double* hv = tile + (size_t)H * H;                              // [2][FW_SMAX] weights of the staged cell
+  int* hi = reinterpret_cast<int*>(hv + 2 * FW_SMAX);             // [2][FW_SMAX] hub indices
+  __shared__ int hcnt[2];
+  for (int t = threadIdx.x; t < H * H; t += 256) tile[t] = 0.0;
+  const int c0 = blockIdx.x * GRAM_HUB_CELLS;
+  const int c1 = min(n, c0 + GRAM_HUB_CELLS);
+  int buf = 0;
+  for (int j = c0; j < c1; ++j, buf ^= 1) {
+    // warp 0 compacts the hub slots of cell j (slot order) into buffer `buf`
+    if (threadIdx.x < 32) {
+      const int cnt = a_cnt[j];
+      int w = 0;
+      for (int s0 = 0; s0 < cnt; s0 += 32) {
+        const int s = s0 + threadIdx.x;
+        int h = -1;
+        double v = 0.0;
+        if (s < cnt) {
+          h = hub_of[a_idx[(size_t)j * S + s]];
+          v = a_val[(size_t)j * S + s];
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, h >= 0);
+        if (h >= 0) {
+          const int pos = w + __popc(ball & ((1u << threadIdx.x) - 1u));
+          hi[buf * FW_SMAX + pos] = h;
+          hv[buf * FW_SMAX + pos] = v;
+        }
+        w += __popc(ball);
       }
-  }
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int st = 128; st > 0; st >>= 1) {
-    if (threadIdx.x < st) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + st]);
+      if (threadIdx.x == 0) hcnt[buf] = w;
+    }
     __syncthreads();
+    const int m = hcnt[buf];
+    for (int e = threadIdx.x; e < m * m; e += 256) {
+      const int p = e / m, q = e - p * m;
+      double* dst = tile + (size_t)hi[buf * FW_SMAX + p] * H + hi[buf * FW_SMAX + q];
+      *dst = __dadd_rn(*dst, __dmul_rn(hv[buf * FW_SMAX + p], hv[buf * FW_SMAX + q]));
+    }
+    // the next iteration stages into the other buffer; its __syncthreads orders these adds before the adds of j+1
   }
-  if (threadIdx.x == 0) {
-    t1[(size_t)l * k + l2] = sh[0];
-    t1[(size_t)l2 * k + l] = sh[0];
-  }
+  __syncthreads();
+  double* out = tiles + (size_t)blockIdx.x * H * H;
+  for (int t = threadIdx.x; t < H * H; t += 256) out[t] = tile[t];
+}
+__global__ void k_gram_hub_reduce(int k, int H, int ntiles, const int* __restrict__ hubs,
+                                  const double* __restrict__ tiles, double* __restrict__ t1) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= H * H) return;
+  double acc = 0.0;
+  for (int c = 0; c < ntiles; ++c) acc = __dadd_rn(acc, tiles[(size_t)c * H * H + e]);
+  const int p = e / H, q = e - p * H;
+  t1[(size_t)hubs[p] * k + hubs[q]] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ candidates by archetype
@@ -1392,27 +1419,41 @@ int sc_fit::update_B_begin() {
     SC_CUDA(ctx, cudaMemcpyAsync(hptr.data(), arow_ptr.p, sizeof(long long) * ((size_t)k + 1), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<int> hubs;
-    std::vector<unsigned char> ishub(k, 0);
+    std::vector<std::pair<long long, int>> cand_h;
     for (int a = 0; a < k; ++a)
-      if (hptr[a + 1] - hptr[a] > hub_thr) {
-        hubs.push_back(a);
-        ishub[a] = 1;
-      }
+      if (hptr[a + 1] - hptr[a] > hub_thr) cand_h.push_back({-(hptr[a + 1] - hptr[a]), a});
+    std::sort(cand_h.begin(), cand_h.end());
+    if ((int)cand_h.size() > GRAM_HUB_MAX) cand_h.resize(GRAM_HUB_MAX);  // the rest stay ordinary (sequential) rows
+    std::vector<int> hubs;
+    for (auto& c : cand_h) hubs.push_back(c.second);
+    std::sort(hubs.begin(), hubs.end());
+    std::vector<unsigned char> ishub(k, 0);
+    std::vector<int> hubof(k, -1);
+    for (size_t q = 0; q < hubs.size(); ++q) {
+      ishub[hubs[q]] = 1;
+      hubof[hubs[q]] = (int)q;
+    }
     last_hubs = (int)hubs.size();
-    SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, hub_thr, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,
+    SC_TRY(hub_flag.ensure(ctx, (size_t)k));
+    SC_CUDA(ctx, cudaMemcpyAsync(hub_flag.p, ishub.data(), (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+    SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, hub_flag.p, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,
               a_val[cur].p, a_cnt[cur].p, t1B.p);
     if (!hubs.empty()) {
       const int H = (int)hubs.size();
+      const int ntiles = (n + GRAM_HUB_CELLS - 1) / GRAM_HUB_CELLS;
       SC_TRY(hub_list.ensure(ctx, (size_t)H));
-      SC_TRY(hub_flag.ensure(ctx, (size_t)k));
+      SC_TRY(gram_hubof.ensure(ctx, (size_t)k));
+      SC_TRY(gram_tiles.ensure(ctx, (size_t)ntiles * H * H));
       SC_CUDA(ctx, cudaMemcpyAsync(hub_list.p, hubs.data(), sizeof(int) * H, cudaMemcpyHostToDevice, ctx->stream));
-      SC_CUDA(ctx, cudaMemcpyAsync(hub_flag.p, ishub.data(), (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+      SC_CUDA(ctx, cudaMemcpyAsync(gram_hubof.p, hubof.data(), sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
       SC_LAUNCH(ctx, k_gram_mirror, dim3((k + 255) / 256, H), 256, 0, k, H, hub_list.p, hub_flag.p, t1B.p);
-      SC_LAUNCH(ctx, k_gram_hubpair, H * (H + 1) / 2, 256, 0, k, S, H, hub_list.p, arow_ptr.p, gk_out.p, gv_out.p,
-                a_idx[cur].p, a_val[cur].p, a_cnt[cur].p, t1B.p);
-      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+      const size_t smem = (size_t)H * H * sizeof(double) + 2 * FW_SMAX * (sizeof(double) + sizeof(int));
+      SC_CUDA(ctx, cudaFuncSetAttribute(k_gram_hub_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SC_LAUNCH(ctx, k_gram_hub_tiles, ntiles, 256, smem, n, S, H, gram_hubof.p, a_idx[cur].p, a_val[cur].p,
+                a_cnt[cur].p, gram_tiles.p);
+      SC_LAUNCH(ctx, k_gram_hub_reduce, (H * H + 255) / 256, 256, 0, k, H, ntiles, hub_list.p, gram_tiles.p, t1B.p);
     }
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
   }
   pstop(P_GRAM);
   // ---- t2 = K A^T as per-cell rows, then as per-archetype candidate lists

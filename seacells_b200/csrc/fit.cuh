@@ -11,7 +11,8 @@ struct sc_fit {
   int row_begin = 0, row_end = 0;  // cells owned by this rank (whole range on one GPU)
   long long nchunks_cur = 0;
   bool in_update_B = false;
-  DBuf<int> hub_ids, hub_slot;
+  DBuf<int> hub_ids, hub_slot, gram_hubof;
+  DBuf<double> gram_tiles;
   DBuf<double> T1H, T2H, hub_part;
   int n_hub = 0, n_hub_pad = 0, last_hub_block = 0;
   DBuf<double> part_out;  // [k][4] per-archetype partial result of one Frank-Wolfe step of _updateB on this rank

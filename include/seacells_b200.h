@@ -72,6 +72,12 @@ void sc_kernel_free(sc_kernel* km);
 int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, const int32_t* indices,
                     const double* data, const double* X, double* Y);
 
+/* ---- next row: greedy initialisation  (cpu.py:342-423 _get_greedy_centers) ---------------------------------------- */
+/* Greedy adaptive column-subset selection on K = M M^T; M as CSR (host or device pointers), centers_out: host int64
+ * [n_centers].  Keeps the reference's dense (n_centers x n) fp64 work matrix, so SC_ERR_CAPACITY when that does not fit. */
+int sc_greedy_centers(sc_ctx* ctx, int n, const int32_t* indptr, const int32_t* indices, const double* data,
+                      long long nnz, int n_centers, int64_t* centers_out);
+
 /* ---- hot path 2: Frank-Wolfe fit  (cpu.py:204-285, 425-536, 558-651) -------------------------------------------- */
 int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out);
 void sc_fit_destroy(sc_fit* fit);
@@ -119,6 +125,9 @@ int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsil
                double* threshold_inout, int* n_iter_out, int* converged_out, double* rss_out, int rss_cap,
                int* n_rss_out);
 
+/* K B as CSR (n x k, int64 indptr): its transpose is Z_ = B_.T @ K (cpu.py:641, get_archetype_matrix cpu.py:680).
+ * Call once with null arrays to learn nnz, then with buffers. */
+int sc_fit_get_KB(sc_fit* fit, long long* nnz_out, int64_t* indptr, int32_t* indices, double* data);
 /* compressed results: idx/val [cols x S], cnt [cols]; column j of A_ is cell j, column a of B_ is archetype a */
 int sc_fit_slots(sc_fit* fit); /* S */
 int sc_fit_get_A(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt);

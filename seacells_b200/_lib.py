@@ -37,6 +37,7 @@ SIGNATURES = {
     "sc_kernel_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sc_kernel_free": (None, [_vp]),
     "sc_spmm_csr_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sc_greedy_centers": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _vp]),
     "sc_fit_create": (_i, [_vp, _i, _i, _i, _pp]),
     "sc_fit_destroy": (None, [_vp]),
     "sc_fit_set_kernel": (_i, [_vp, _vp, _vp, _vp, _ll]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     "sc_fit_update_B_step": (_i, [_vp, _i, _vp, _i]),
     "sc_fit_update_B_end": (_i, [_vp]),
     "sc_fit_run": (_i, [_vp, _i, _i, _d, _d, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp, _i, C.POINTER(_i)]),
+    "sc_fit_get_KB": (_i, [_vp, C.POINTER(_ll), _vp, _vp, _vp]),
     "sc_fit_slots": (_i, [_vp]),
     "sc_fit_get_A": (_i, [_vp, _vp, _vp, _vp]),
     "sc_fit_get_B": (_i, [_vp, _vp, _vp, _vp]),

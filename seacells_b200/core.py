@@ -250,6 +250,17 @@ class FitEngine:
         """B_ (n x k), CSR."""
         return self._slots_to_csc(*self.B_slots(), self.n).tocsr()
 
+    def KB(self) -> sp.csr_matrix:
+        """K @ B_ (n x k) from the device; Z_ = B_.T @ K is its transpose (cpu.py:641)."""
+        nnz = C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.sc_fit_get_KB(self.h, C.byref(nnz), None, None, None), "sc_fit_get_KB")
+        indptr = np.empty(self.n + 1, np.int64)
+        indices = np.empty(nnz.value, np.int32)
+        data = np.empty(nnz.value, np.float64)
+        self.ctx.check(self.ctx.lib.sc_fit_get_KB(self.h, C.byref(nnz), ptr(indptr), ptr(indices), ptr(data)),
+                       "sc_fit_get_KB")
+        return sp.csr_matrix((data, indices, indptr), shape=(self.n, self.k))
+
     def hard_assignments(self) -> np.ndarray:
         lab = np.empty(self.n, np.int32)
         self.ctx.check(self.ctx.lib.sc_fit_hard_assignments(self.h, ptr(lab)), "sc_fit_hard_assignments")
@@ -630,9 +641,7 @@ class SEACellsB200:
     def get_archetype_matrix(self):
         """cpu.py:680-682: Z_ = B_.T @ K (k x n)."""
         if self.Z_ is None and self._engine is not None:
-            B = sp.csr_matrix(self.B_)
-            M = self.kernel_matrix
-            Z = (B.T @ M) @ M.T
+            Z = self._engine.KB().T.tocsc()   # (K B)^T = B^T K since K is symmetric; computed on the GPU
             self.Z_ = Z if self.use_sparse else Z.toarray()
         return self.Z_
 

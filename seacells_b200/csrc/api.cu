@@ -6,6 +6,9 @@
 #include "fit.cuh"
 #include "kernel_build.cuh"
 
+int sc_greedy_centers_impl(sc_ctx* ctx, int n, const int* indptr, const int* indices, const double* data, long long nnz,
+                           int n_centers, long long* centers_host);
+
 namespace {
 
 // stage a host-or-device input on the device; `own` keeps the staging buffer alive
@@ -244,6 +247,13 @@ int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, con
   return SC_OK;
 }
 
+int sc_greedy_centers(sc_ctx* ctx, int n, const int32_t* indptr, const int32_t* indices, const double* data,
+                      long long nnz, int n_centers, int64_t* centers_out) {
+  if (!ctx || !indptr || !indices || !data || !centers_out) return SC_ERR_ARG;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sc_greedy_centers_impl(ctx, n, indptr, indices, data, nnz, n_centers, (long long*)centers_out);
+}
+
 // ------------------------------------------------------------------------------------------------ hot path 2
 int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out) {
   if (!ctx || !out) return SC_ERR_ARG;
@@ -366,6 +376,10 @@ int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsil
                   rss_out, rss_cap, n_rss_out);
 }
 
+int sc_fit_get_KB(sc_fit* fit, long long* nnz_out, int64_t* indptr, int32_t* indices, double* data) {
+  if (!fit) return SC_ERR_ARG;
+  return fit->get_KB_csr(nnz_out, (long long*)indptr, indices, data);
+}
 int sc_fit_slots(sc_fit* fit) { return fit ? fit->S : 0; }
 int sc_fit_get_A(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;

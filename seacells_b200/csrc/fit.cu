@@ -1711,6 +1711,43 @@ int sc_fit::run(int max_iter, int min_iter, double eps, double l2, double* thres
   return SC_OK;
 }
 
+__global__ void k_lists_to_csr(int rows, RowLists L, const long long* __restrict__ off, int* __restrict__ indices,
+                               double* __restrict__ data) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const long long p = L.ptr[warp], o = off[warp];
+  const int len = L.len[warp];
+  for (int x = lane; x < len; x += 32) {
+    indices[o + x] = L.key[p + x];
+    data[o + x] = L.val[p + x];
+  }
+}
+
+// K B as CSR (n x k): the transpose of Z_ = B_.T @ K (cpu.py:641).  Pass null pointers to get only nnz.
+int sc_fit::get_KB_csr(long long* nnz_out, long long* indptr, int* indices, double* data) {
+  if (!have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: B has not been initialised");
+  SC_TRY(precompute_A());
+  SC_TRY(t_off.ensure(ctx, (size_t)n + 1));
+  SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, KB.len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));
+  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, t_off.p, (size_t)n + 1, tmp));
+  long long nnz = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&nnz, t_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nnz_out) *nnz_out = nnz;
+  if (!indptr || !indices || !data) return SC_OK;
+  DBuf<int> di;
+  DBuf<double> dv;
+  SC_TRY(di.ensure(ctx, (size_t)nnz + 1));
+  SC_TRY(dv.ensure(ctx, (size_t)nnz + 1));
+  SC_LAUNCH(ctx, k_lists_to_csr, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), t_off.p, di.p, dv.p);
+  SC_CUDA(ctx, sc_copy(indptr, t_off.p, sizeof(long long) * ((size_t)n + 1), ctx->stream));
+  SC_CUDA(ctx, sc_copy(indices, di.p, sizeof(int) * (size_t)nnz, ctx->stream));
+  SC_CUDA(ctx, sc_copy(data, dv.p, sizeof(double) * (size_t)nnz, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
 int sc_fit::get_A(int* idx, double* val, int* cnt) {
   if (!have_A || !a_is_slots) SC_FAIL(ctx, SC_ERR_STATE, "fit: A has not been computed");
   SC_CUDA(ctx, sc_copy(idx, a_idx[a_cur].p, sizeof(int) * (size_t)n * S, ctx->stream));

@@ -94,6 +94,7 @@ struct sc_fit {
   int rss(double* out_host);
   int run(int max_iter, int min_iter, double eps, double l2, double* threshold_inout, int* n_iter_out,
           int* converged_out, double* rss_out, int rss_cap, int* n_rss_out);
+  int get_KB_csr(long long* nnz_out, long long* indptr, int* indices, double* data);
   int get_A(int* idx, double* val, int* cnt);
   int get_B(int* idx, double* val, int* cnt);
   int hard_assignments(int* labels);

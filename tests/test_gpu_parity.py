@@ -288,7 +288,9 @@ def test_model_class_end_to_end():
     assert list(soft_labels.values[:, 0]) == list(ad.obs_names[si[:, 0]])
     np.testing.assert_allclose(model.compute_RSS(), ref["RSS_iters"][-1], rtol=RSS_RTOL)
     Z = model.get_archetype_matrix()
-    assert Z.shape == (k, n)
+    K = model.kernel_matrix @ model.kernel_matrix.T
+    Zo = (ref["B"].T @ K)                                                    # cpu.py:641
+    assert Z.shape == (k, n) and abs(Z - Zo).max() <= 1e-12 * abs(Zo).max()
     # dense flavour (cpu_dense.py): ndarrays out, l2_penalty honoured
     ad2 = MiniAnnData(X)
     md = SEACells(ad2, "X_pca", k, verbose=False, use_sparse=False, l2_penalty=0.02)
@@ -332,3 +334,23 @@ def test_properties_at_scale():
     eng2.set_A(O.l1_normalise_columns(synth_assignments(n, k)))
     rss2, *_ = eng2.run(max_iter=3, min_iter=3)
     assert rss2 == rss and same_sparse(eng2.A(), A) and same_sparse(eng2.B(), B)
+
+
+def test_greedy_initialisation_vs_reference():
+    """cpu.py:342-423 on the GPU: same centres as the unmodified reference (golden) and as the oracle."""
+    from seacells_b200 import SEACells
+    from seacells_b200.greedy import greedy_centers_from_kernel
+    from seacells_b200.synth import MiniAnnData
+    g = load_golden("rna_n600_k8_sparse")
+    M = csr_from(g, "M")
+    c = greedy_centers_from_kernel(M, len(g["greedy_centers"]))
+    assert np.array_equal(c, g["greedy_centers"])
+    X, Mo, _, _ = _seeded_case(2500, 33, seed=4)
+    assert np.array_equal(greedy_centers_from_kernel(Mo, 43), O.greedy_centers(Mo @ Mo.T, 43))
+    # through the model class: waypoint_proportion = 0 -> greedy only (cpu.py:176, 188-201)
+    ad = MiniAnnData(X)
+    model = SEACells(ad, "X_pca", 33, verbose=False, use_sparse=True)
+    model.add_precomputed_kernel_matrix(Mo)
+    model.waypoint_proportion = 0
+    model.initialize_archetypes()
+    assert np.array_equal(model.archetypes, O.greedy_centers(Mo @ Mo.T, 43)[:33])

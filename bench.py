@@ -130,7 +130,7 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                             "host_cores_available": os.cpu_count()},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 def workload_name(n):
@@ -274,12 +274,24 @@ def run_ours(args):
                             "sample": f"full fit() ({cpu_iters} outer iterations) of the oracle restatement of "
                                       f"cpu.SEACellsCPU on a {cpu_n}-cell x 50-PC sample (k={cpu_k}); scipy sparse, "
                                       f"single thread; {os.cpu_count()} host cores available"}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(obj):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, library prints) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # NCCL prints its version banner on fd 1; keep the contract's stdout to exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

@@ -103,6 +103,7 @@ struct UpdAArgs {
   double l2;
   RowLists KB;        // candidates of cell j: (archetype, t2[archetype, j]) sorted by archetype
   const double* t1T;  // t1T[i' * k + i] = t1[i, i']
+  const int* perm;    // locality order of the rank's cells (see k_perm_keys)
   RowLists Aprev;
   int* a_idx;
   double* a_val;
@@ -599,7 +600,8 @@ __global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restric
 }
 
 // out[cta][slot][4] = {candidate min G, cell, non-candidate min G, cell} over the CTA's cells
-__global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end, int nh_pad, RowLists KB,
+__global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end, int nh_pad,
+                                                     const int* __restrict__ perm, RowLists KB,
                                                      const double* __restrict__ T1H, const double* __restrict__ T2H,
                                                      double* __restrict__ out) {
   __shared__ double s_v[8][2][HUB_MAX];
@@ -615,7 +617,8 @@ __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end,
   }
   const int c0 = row_begin + blockIdx.x * HUB_CELLS_PER_CTA;
   const int c1 = min(row_end, c0 + HUB_CELLS_PER_CTA);
-  for (int i = c0 + warp; i < c1; i += 8) {
+  for (int ii = c0 + warp; ii < c1; ii += 8) {
+    const int i = perm[ii - row_begin];  // locality order; ties below are resolved on the cell index explicitly
     const long long p = KB.ptr[i];
     const int L = KB.len[i];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -644,11 +647,11 @@ __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end,
         const double t2v = t2row[r * 32];
         const double G = 2.0 * (acc[r] - t2v);
         if (t2v > 0.0) {
-          if (G < cv[r]) {  // cells ascend within a warp: strict '<' keeps the first index
+          if (G < cv[r] || (G == cv[r] && i < ci[r])) {
             cv[r] = G;
             ci[r] = i;
           }
-        } else if (G < nv[r]) {
+        } else if (G < nv[r] || (G == nv[r] && i < ni[r])) {
           nv[r] = G;
           ni[r] = i;
         }
@@ -734,6 +737,18 @@ __device__ __forceinline__ void block_argmin_256(double& v, int& i, double* sg, 
       v = sg[w];
       i = si[w];
     }
+}
+
+// Locality order: cells sorted by the archetype of their largest K B entry.  Kernels that gather rows of a k x k matrix
+// (or of its hub slice) per cell walk the cells in this order so that neighbouring warps hit the same rows in L1/L2.
+__global__ void k_perm_keys(int row_begin, int row_end, const int* __restrict__ lmax, unsigned long long* __restrict__ keys) {
+  const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= row_end) return;
+  keys[i - row_begin] = ((unsigned long long)(unsigned)lmax[i] << 32) | (unsigned)i;
+}
+__global__ void k_perm_unpack(int count, const unsigned long long* __restrict__ keys, int* __restrict__ perm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) perm[t] = (int)(keys[t] & 0xffffffffu);
 }
 
 // largest entry of every K B row: (value, archetype); feeds the second pruning bound of k_updateB_eval
@@ -1323,6 +1338,24 @@ int sc_fit::compute_KB(int r0, int r1, bool sorted) {
   return SC_OK;
 }
 
+// perm = this rank's cells sorted by (archetype of the largest entry of the current K B row, cell)
+int sc_fit::build_perm() {
+  const int nloc = row_end - row_begin;
+  SC_TRY(cmax_v.ensure(ctx, (size_t)n));
+  SC_TRY(cmax_l.ensure(ctx, (size_t)n));
+  SC_TRY(perm.ensure(ctx, (size_t)nloc + 1));
+  SC_TRY(pk_in.ensure(ctx, (size_t)nloc + 1));
+  SC_TRY(pk_out.ensure(ctx, (size_t)nloc + 1));
+  if (nloc == 0) return SC_OK;
+  SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
+  SC_LAUNCH(ctx, k_perm_keys, (nloc + 255) / 256, 256, 0, row_begin, row_end, cmax_l.p, pk_in.p);
+  int kb = 1;
+  while ((1ll << kb) < k) kb++;
+  SC_TRY(sc_sort_keys_u64(ctx, pk_in.p, pk_out.p, (size_t)nloc, 32 + kb, tmp));
+  SC_LAUNCH(ctx, k_perm_unpack, (nloc + 255) / 256, 256, 0, nloc, pk_out.p, perm.p);
+  return SC_OK;
+}
+
 int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
@@ -1349,6 +1382,7 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   g.l2 = l2;
   g.KB = KB.view();
   g.t1T = t1A.p;
+  g.perm = nullptr;  // measured: walking the cells in locality order makes this kernel slower (hot t1 rows), not faster
   g.Aprev = A_view();
   g.a_idx = a_idx[nxt].p;
   g.a_val = a_val[nxt].p;
@@ -1579,6 +1613,7 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     ev_b.push_back(eb);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
+  if (t == 0 && n_hub > 0) SC_TRY(build_perm());  // the order only affects locality; reused for the remaining steps
   if (nchunks > 0) {
     SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
     SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
@@ -1589,7 +1624,8 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (n_hub > 0) {
     const int nloc = row_end - row_begin;
     const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
-    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, KB.view(), T1H.p, T2H.p, hub_part.p);
+    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, KB.view(), T1H.p, T2H.p,
+              hub_part.p);
     SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));

@@ -11,7 +11,8 @@ struct sc_fit {
   int row_begin = 0, row_end = 0;  // cells owned by this rank (whole range on one GPU)
   long long nchunks_cur = 0;
   bool in_update_B = false;
-  DBuf<int> hub_ids, hub_slot, gram_hubof;
+  DBuf<int> hub_ids, hub_slot, gram_hubof, perm;
+  DBuf<unsigned long long> pk_in, pk_out;
   DBuf<double> gram_tiles;
   DBuf<double> T1H, T2H, hub_part;
   int n_hub = 0, n_hub_pad = 0, last_hub_block = 0;
@@ -83,6 +84,7 @@ struct sc_fit {
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
   int compute_KB(int r0, int r1, bool sorted);
+  int build_perm();
   int set_shard(int r0, int r1);
   int update_B_begin();
   int update_B_eval(int t, double* partial_dev);

@@ -1,0 +1,141 @@
+"""Reference-facing behaviour of the model class and less common parameter values, against the oracle."""
+import os
+import pickle
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import seacells_oracle as O
+from tests.helpers import same_sparse
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d=50, seed=0, kind="rna"):
+    from seacells_b200.synth import synth_embedding
+    X = synth_embedding(n, d, seed, kind)
+    M, *_ = O.build_kernel(X.astype(np.float64), 15)
+    return X, M
+
+
+@pytest.mark.parametrize("T", [1, 7, 64])
+def test_other_max_FW_iter(T):
+    from seacells_b200 import FitEngine
+    from seacells_b200.synth import synth_archetypes, synth_assignments
+    n, k = 900, 12
+    X, M = _data(n, seed=5)
+    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
+    ref = O.fit(M, arch, A0, max_iter=3, min_iter=3, max_FW_iter=T)
+    eng = FitEngine(n, k, T)
+    eng.set_kernel(M)
+    eng.set_archetypes(arch)
+    eng.set_A(O.l1_normalise_columns(A0))
+    rss, n_iter, conv, _ = eng.run(max_iter=3, min_iter=3)
+    assert same_sparse(eng.A(), ref["A"]) and same_sparse(eng.B(), ref["B"])
+    np.testing.assert_allclose(rss, ref["RSS_iters"], rtol=1e-9)
+    with pytest.raises(Exception):
+        FitEngine(n, k, 65)          # compile-time limit of the kernels, reported instead of mis-computing
+
+
+def test_tiny_k_and_duplicate_cells():
+    from seacells_b200 import FitEngine, build_kernel
+    rng = np.random.default_rng(3)
+    n = 403
+    X = rng.normal(size=(n, 9)).astype(np.float32)
+    # eleven copies of one cell: fewer than n_neighbors//2 non-zero distances remain, so sigma = 0 and the reference
+    # produces NaN on those diagonals (0/0) and drops the -inf exponents; the engine must do exactly the same
+    Xd = X.copy()
+    Xd[50:60] = Xd[49]
+    M, sigma, idx, d2 = build_kernel(Xd, 15).export()
+    with np.errstate(all="ignore"):
+        Mo, so, io, do = O.build_kernel(Xd.astype(np.float64), 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do) and np.array_equal(sigma, so) and (so == 0).sum() == 11
+    assert np.array_equal(M.indptr, Mo.indptr) and np.array_equal(M.indices, Mo.indices)
+    assert np.isnan(Mo.data).sum() == 11 and np.allclose(M.data, Mo.data, rtol=1e-13, atol=0, equal_nan=True)
+    X[50:54] = X[49]                 # five copies: zero distances are dropped from the graph, sigma stays positive
+    km = build_kernel(X, 15)
+    M, sigma, idx, d2 = km.export()
+    Mo, so, io, do = O.build_kernel(X.astype(np.float64), 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do) and np.array_equal(sigma, so)
+    assert np.array_equal(M.indices, Mo.indices) and np.allclose(M.data, Mo.data, rtol=1e-13, atol=0)
+    for k in (2, 3):
+        arch = np.arange(k) * 100 + 7
+        A0 = sp.csr_matrix(rng.random((k, n)))
+        ref = O.fit(Mo, arch, A0, max_iter=2, min_iter=2)
+        eng = FitEngine(n, k)
+        eng.set_kernel(Mo)
+        eng.set_archetypes(arch)
+        eng.set_A(O.l1_normalise_columns(A0))
+        rss, *_ = eng.run(max_iter=2, min_iter=2)
+        assert same_sparse(eng.A(), ref["A"]) and same_sparse(eng.B(), ref["B"])
+        np.testing.assert_allclose(rss, ref["RSS_iters"], rtol=1e-9)
+
+
+def test_default_random_initialisation_follows_the_legacy_rng_stream():
+    """cpu.py:257-264: without initial_assignments A0 comes from np.random (randint then random)."""
+    from seacells_b200 import SEACells
+    from seacells_b200.synth import MiniAnnData, synth_archetypes
+    n, k = 700, 9
+    X, M = _data(n, seed=8)
+    arch = synth_archetypes(n, k)
+    np.random.seed(42)
+    per = int(k * 0.25)
+    r = np.random.randint(0, k, size=(n, per)).reshape(-1)
+    A0 = sp.csr_matrix((np.random.random(len(r)), (r, np.repeat(np.arange(n), per))), shape=(k, n))
+    ref = O.fit(M, arch, A0, max_iter=2, min_iter=2)
+    model = SEACells(MiniAnnData(X), "X_pca", k, verbose=False, use_sparse=True)
+    model.add_precomputed_kernel_matrix(M)
+    np.random.seed(42)
+    try:
+        model.fit(max_iter=2, min_iter=2, initial_archetypes=arch)
+    except RuntimeWarning:
+        pass
+    assert same_sparse(model.A_, ref["A"]) and same_sparse(model.B_, ref["B"])
+    assert same_sparse(model.A0, O.l1_normalise_columns(A0))
+
+
+def test_step_explicit_updates_and_persistence():
+    from seacells_b200 import SEACells
+    from seacells_b200.synth import MiniAnnData, synth_archetypes, synth_assignments
+    n, k = 800, 10
+    X, M = _data(n, d=30, seed=2, kind="atac")
+    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
+    ad = MiniAnnData(X.astype(np.float64), key="X_svd")          # float64 embedding under the scATAC key
+    model = SEACells(ad, "X_svd", k, verbose=False, use_sparse=True, convergence_epsilon=1e-5)
+    with pytest.raises(RuntimeError):
+        model.step()                                                  # cpu.py:566-579
+    model.construct_kernel_matrix(graph_construction="intersection")
+    Mi, *_ = O.build_kernel(X.astype(np.float64), 15, "intersection")
+    assert np.array_equal(model.kernel_matrix.indices, Mi.indices)
+    assert "distances" in ad.obsp and ad.obsp["distances"].shape == (n, n)
+    with pytest.raises(ValueError):
+        model.construct_kernel_matrix(graph_construction="nonsense")
+    model.construct_kernel_matrix()                                   # back to the union graph
+    with pytest.raises(RuntimeError):
+        model.step()                                                  # not initialised yet
+    model.initialize(initial_archetypes=arch, initial_assignments=A0)
+    K = model.kernel_matrix @ model.kernel_matrix.T
+    A = O.update_A(K, sp.csr_matrix((np.ones(k), (arch, np.arange(k))), shape=(n, k)), O.l1_normalise_columns(A0))
+    assert same_sparse(model.A_, A)
+    thr = model.convergence_threshold
+    model.step()
+    model.step()                                                      # "resume" = call step() again
+    assert len(model.RSS_iters) == 3 and model.convergence_threshold == thr
+    assert list(ad.obs["SEACell"]) == list(model.get_hard_assignments()["SEACell"])
+    # explicit-matrix entry points (cpu.py:425, 461) agree with the stateful path
+    A_now, B_now = model.A_, model.B_
+    B_next = O.update_B(K, A_now, B_now)
+    assert same_sparse(model._updateB(A_now, B_now), B_next)
+    assert same_sparse(model._updateA(B_next, A_now), O.update_A(K, B_next, A_now))
+    np.testing.assert_allclose(model.compute_RSS(A_now, B_now), O.compute_RSS(model.kernel_matrix, A_now, B_now), rtol=1e-9)
+    R = model.compute_reconstruction(A_now, B_now)
+    assert R.shape == (n, n)
+    with tempfile.TemporaryDirectory() as d:
+        model.save_assignments(d)                                     # cpu.py:743-764
+        assert sorted(os.listdir(d)) == ["A.npz", "B.npz", "SEACells.csv", "kernel_matrix.npz"]
+        assert sp.load_npz(os.path.join(d, "A.npz")).shape == (n, k)  # A.npz holds A_.T
+        model.save_model(d)                                           # cpu.py:731-741
+        m2 = pickle.load(open(os.path.join(d, "model.pkl"), "rb"))
+        assert m2.RSS_iters == model.RSS_iters and m2.k == k

@@ -46,6 +46,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(n, world):
+    """DRAM bytes per launch group from the committed ncu --set full capture (1M cells, 1 GPU only)."""
+    p = os.path.join(ROOT, "profiles", "r1_updB_group_traffic.json")
+    if n == 1_000_000 and world == 1 and os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch_group"])
+        except Exception:
+            return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -248,13 +259,16 @@ def run_ours(args):
     alg_bytes = 12.0 * st1["t2_nnz_last_update_B"] + 12.0 * st1["kb_nnz_last"] + 16.0 * n / world  # rank 0's shard
     peak, peak_src = _peaks()
     achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_updateB_eval (+k_row_max): gradient of _updateB on the support of t2",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm",
+                "kernel": "gradient of _updateB on the support of t2: k_row_max + k_updateB_eval (2 rounds) + "
+                          "k_updateB_hub (+reduce), one launch group per Frank-Wolfe step",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(n, world),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": per_launch_s * 1e3, "launches_timed": steps_timed,
                 "share_of_step": eval_s / t_dev if t_dev > 0 else None,
                 "bytes_definition": "12 B x nnz(t2) candidate (cell, t2) pairs + 12 B x nnz(K B) row entries + 16 B x n "
-                                    "row maxima, each moved once per Frank-Wolfe step"}
+                                    "row maxima, each moved once per Frank-Wolfe step (rank 0's shard when N > 1)",
+                "traffic_note": "ncu dram bytes of the two largest kernels of the group are in profiles/*.summary.txt"}
     cpu_n = 2500
     cpu_dt, cpu_iters, cpu_k = cpu_fit_sample(cpu_n)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

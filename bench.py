@@ -144,8 +144,8 @@ def run_reference(args):
     _emit(out)
 
 
-def workload_name(n):
-    return (f"synthetic {n} cells x 50 PCs (Gaussian mixture, decaying spectrum), n_SEACells={n // 75}, n_neighbors=15, "
+def workload_name(n, pcs=50):
+    return (f"synthetic {n} cells x {pcs} PCs (Gaussian mixture, decaying spectrum), n_SEACells={n // 75}, n_neighbors=15, "
             f"union graph, fit(min_iter=10, max_iter=100, eps=1e-3, max_FW_iter=50), given archetypes + sparse A0")
 
 
@@ -174,7 +174,7 @@ def run_ours(args):
     from seacells_b200.parallel import ShardedFit, sharded_knn
     n = args.cells
     k = n // 75
-    X = synth_embedding(n, 50, seed=0)
+    X = synth_embedding(n, args.pcs, seed=0, kind=args.kind)
     t0 = time.perf_counter()
     knn_graph = sharded_knn(X, 15, ctx) if world > 1 else None
     km = build_kernel(X, 15, "union", ctx, knn_graph=knn_graph)
@@ -275,7 +275,7 @@ def run_ours(args):
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(n), "cells_per_gpu": n // world if world > 1 else n, "outer_iterations": n_iter,
+           "config": {"workload": workload_name(n, args.pcs), "cells_per_gpu": n // world if world > 1 else n, "outer_iterations": n_iter,
                       "converged": bool(conv), "rss_first_last": [rss[0], rss[-1]],
                       "fit_seconds": t_dev / args.steps, "construct_kernel_matrix_s": t_build,
                       "l2_policy": "inputs (>= 1 GB of lists per step) exceed the 126 MB L2; no explicit flush",
@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=1_000_000)
+    ap.add_argument("--pcs", type=int, default=50, help="embedding dimensions (30 for the scATAC-like config 3)")
+    ap.add_argument("--kind", default="rna", choices=["rna", "atac"], help="noise spectrum of the synthetic embedding")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -139,8 +139,8 @@ int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells /* [k] */);
 /* get_soft_assignments (cpu_dense.py:586-605): `top` rounds of argmax with masking; idx/w [n x top] */
 int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
 /* diagnostics: [0] cells that took the generic path in the last _updateA, [1] nnz(t2) of the last _updateB,
- * [2] hub archetypes (rows of A longer than 8192 cells) in the last _updateB, [3] rows of the last K*B product that
- * needed the dense-accumulator kernel, [4] (cell, archetype) gradients evaluated exactly in the last _updateB (all
+ * [2] archetypes in the cell-major hub block of the last _updateB, [3] rows (cumulative over the life of the handle)
+ * that needed the dense-accumulator kernel of the sparse product, [4] (cell, archetype) gradients evaluated exactly in the last _updateB (all
  * Frank-Wolfe steps together; the rest of nnz(t2) x max_FW_iter was pruned by the lower bounds), [5] Frank-Wolfe
  * steps of _updateB timed so far and [6] their summed CUDA-event time in ns for the gradient kernel (row max + both
  * rounds of k_updateB_eval), [7] nnz of the last K*B row lists.  out: 8 values. */

@@ -281,7 +281,7 @@ class FitEngine:
         out = np.zeros(8, np.int64)
         self.ctx.check(self.ctx.lib.sc_fit_stats(self.h, ptr(out)), "sc_fit_stats")
         return {"slow_cells_last_update_A": int(out[0]), "t2_nnz_last_update_B": int(out[1]),
-                "hub_archetypes_last_update_B": int(out[2]), "dense_rows_last_spgemm": int(out[3]),
+                "hub_archetypes_last_update_B": int(out[2]), "dense_rows_spgemm_total": int(out[3]),
                 "gradients_evaluated_last_update_B": int(out[4]), "updB_steps_timed": int(out[5]),
                 "updB_eval_ns_total": int(out[6]), "kb_nnz_last": int(out[7])}
 

@@ -410,7 +410,7 @@ int sc_fit_stats(sc_fit* fit, long long* out4) {
   out4[0] = fit->last_slow_cells;
   out4[1] = fit->last_t2_nnz;
   out4[2] = fit->last_hub_block;
-  out4[3] = fit->sp.last_big_rows;
+  out4[3] = fit->sp.total_big_rows;
   return SC_OK;
 }
 int sc_fit_profile(sc_fit* fit, double* out16) {

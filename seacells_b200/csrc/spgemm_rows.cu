@@ -417,6 +417,7 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
   SC_CUDA(ctx, cudaMemcpyAsync(&nbig, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   sc.last_big_rows = nbig;
+  sc.total_big_rows += nbig;
   if (nbig > 0) {
     const int bgrid = std::min(nbig, 148 * 2);
     SC_TRY(sc.big_acc.ensure(ctx, (size_t)bgrid * key_space));

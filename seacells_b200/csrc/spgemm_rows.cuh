@@ -7,6 +7,7 @@ struct SpgemmScratch {
   DBuf<double> big_acc;
   DBuf<char> tmp;
   int last_big_rows = 0;
+  long long total_big_rows = 0;  // cumulative over all products of this scratch
 };
 
 // Z[i,:] = sum_q S[i,q] * X[q,:] for rows i in [row_begin,row_end); other rows of Z are empty.  Rows sorted by key.

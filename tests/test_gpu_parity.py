@@ -354,3 +354,50 @@ def test_greedy_initialisation_vs_reference():
     model.waypoint_proportion = 0
     model.initialize_archetypes()
     assert np.array_equal(model.archetypes, O.greedy_centers(Mo @ Mo.T, 43)[:33])
+
+
+def test_many_candidates_and_wide_rows():
+    """Paths that only dense neighbourhoods with many archetypes reach: cells with > 128 candidate archetypes (generic
+    _updateA kernel) and K*B rows with > 448 distinct archetypes (dense-accumulator rows of the sparse product)."""
+    from seacells_b200.synth import synth_archetypes, synth_assignments
+    n, k, d = 1400, 900, 12
+    X = np.random.default_rng(1).normal(size=(n, d)).astype(np.float32)     # one blob: K has ~280 entries per row
+    M, *_ = O.build_kernel(X.astype(np.float64), 15)
+    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
+    K = M @ M.T
+    B = sp.csr_matrix((np.ones(k), (arch, np.arange(k))), shape=(n, k))
+    A = O.l1_normalise_columns(A0)
+    eng = _engine(n, k)
+    eng.set_kernel(M)
+    eng.set_archetypes(arch)
+    eng.set_A(A)
+    A = O.update_A(K, B, A, 50)
+    eng.update_A(0.0)
+    assert eng.stats()["slow_cells_last_update_A"] > 1000
+    assert same_sparse(eng.A(), A)
+    B = O.update_B(K, A, B, 50)
+    eng.update_B()
+    assert same_sparse(eng.B(), B)
+    A = O.update_A(K, B, A, 50)
+    eng.update_A(0.0)
+    assert same_sparse(eng.A(), A)
+    np.testing.assert_allclose(eng.rss(), O.compute_RSS(M, A, B), rtol=RSS_RTOL)
+    assert eng.stats()["dense_rows_spgemm_total"] > 0
+
+
+@pytest.mark.slow
+def test_config1_10k_cells_two_outer_iterations():
+    """BASELINE config 1 size (10k cells, k=133): reaches the hub rows of the Gram kernel (> 8192 cells per row) and
+    the hub block of _updateB; A and B must still equal the oracle's bit for bit."""
+    n, k = 10000, 133
+    X, M, arch, A0 = _seeded_case(n, k, seed=0)
+    ref = O.fit(M, arch, A0, max_iter=2, min_iter=2)
+    eng = _engine(n, k)
+    eng.set_kernel(M)
+    eng.set_archetypes(arch)
+    eng.set_A(O.l1_normalise_columns(A0))
+    rss, n_iter, conv, _ = eng.run(max_iter=2, min_iter=2)
+    assert eng.stats()["hub_archetypes_last_update_B"] > 0
+    np.testing.assert_allclose(rss, ref["RSS_iters"], rtol=RSS_RTOL)
+    assert same_sparse(eng.A(), ref["A"]) and same_sparse(eng.B(), ref["B"])
+    assert np.array_equal(eng.hard_assignments(), ref["labels"])

@@ -90,6 +90,32 @@ def test_emulated_shards_reproduce_the_reference(world):
         assert np.array_equal(e.hard_assignments(), g["labels"])
 
 
+def test_emulated_shards_with_hub_archetypes():
+    """5000 cells: hub archetypes exist, so the cell-major hub block and the per-rank hub selection are exercised;
+    the sharded result must equal the single-engine result bit for bit."""
+    from seacells_b200 import FitEngine
+    from seacells_b200.synth import synth_archetypes, synth_assignments, synth_embedding
+    n, k = 5000, 66
+    X = synth_embedding(n, 50, 0)
+    M, *_ = O.build_kernel(X.astype(np.float64), 15)
+    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
+    g = {"M_data": M.data, "M_indices": M.indices.astype(np.int32), "M_indptr": M.indptr.astype(np.int64),
+         "M_shape": np.array(M.shape), "k": k, "T": 50, "archetypes": arch, "n_iter": 2}
+    A0c = sp.csr_matrix(A0)
+    g.update({"A0_data": A0c.data, "A0_indices": A0c.indices.astype(np.int32), "A0_indptr": A0c.indptr.astype(np.int64),
+              "A0_shape": np.array(A0c.shape)})
+    engs, rss = _emulated_fit(g, 3)
+    one = FitEngine(n, k)
+    one.set_kernel(M)
+    one.set_archetypes(arch)
+    one.set_A(O.l1_normalise_columns(A0))
+    rss1, *_ = one.run(max_iter=2, min_iter=2)
+    assert one.stats()["hub_archetypes_last_update_B"] > 0
+    assert rss == rss1
+    for e in engs:
+        assert same_sparse(e.A(), one.A()) and same_sparse(e.B(), one.B())
+
+
 def _nccl_worker(rank, world, port, name, ret):
     import torch
     import torch.distributed as dist

@@ -19,10 +19,9 @@ import types
 import numpy as np
 import scipy.sparse as sp
 
-REF = "/root/reference/SEACells"
-
-
 from oracle.seacells_oracle import knn_exact as exact_knn  # one definition of the kNN stand-in
+
+REF = "/root/reference/SEACells"
 
 
 def _neighbors(ad, use_rep, n_neighbors, knn=True):

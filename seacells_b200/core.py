@@ -127,7 +127,6 @@ class FitEngine:
         self.ctx.check(self.ctx.lib.sc_fit_create(self.ctx.h, self.n, self.k, self.T, C.byref(h)), "sc_fit_create")
         self.h = h
         self.S = int(self.ctx.lib.sc_fit_slots(self.h))
-        self._keep = []
 
     # -- inputs
     def set_kernel(self, M):

@@ -103,7 +103,6 @@ struct UpdAArgs {
   double l2;
   RowLists KB;        // candidates of cell j: (archetype, t2[archetype, j]) sorted by archetype
   const double* t1T;  // t1T[i' * k + i] = t1[i, i']
-  const int* perm;    // locality order of the rank's cells (see k_perm_keys)
   RowLists Aprev;
   int* a_idx;
   double* a_val;
@@ -428,7 +427,7 @@ __global__ void k_row_bounds(int k, const unsigned long long* __restrict__ keys,
 }
 // t1B[l][a] = sum_j A[l,j] A[a,j], cells j ascending (the order of scipy's csr_matmat for A @ A.T, cpu.py:480).
 // Rows longer than `hub_thr` cells ("hub" archetypes: low-index archetypes that collect a little weight from almost
-// every cell through the argmin-of-zeros rule) are skipped here and filled by k_gram_mirror / k_gram_hubpair.
+// every cell through the argmin-of-zeros rule) are skipped here and filled by k_gram_mirror / k_gram_hub_tiles.
 __global__ void k_gram(int k, int S, const unsigned char* __restrict__ is_hub, const long long* __restrict__ rptr,
                        const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
                        const int* __restrict__ a_idx, const double* __restrict__ a_val,
@@ -1382,7 +1381,7 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   g.l2 = l2;
   g.KB = KB.view();
   g.t1T = t1A.p;
-  g.perm = nullptr;  // measured: walking the cells in locality order makes this kernel slower (hot t1 rows), not faster
+  // (walking the cells in the locality order of build_perm() was measured slower here: hot t1 rows collide in L2)
   g.Aprev = A_view();
   g.a_idx = a_idx[nxt].p;
   g.a_val = a_val[nxt].p;
@@ -1467,7 +1466,6 @@ int sc_fit::update_B_begin() {
       ishub[hubs[q]] = 1;
       hubof[hubs[q]] = (int)q;
     }
-    last_hubs = (int)hubs.size();
     SC_TRY(hub_flag.ensure(ctx, (size_t)k));
     SC_CUDA(ctx, cudaMemcpyAsync(hub_flag.p, ishub.data(), (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
     SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, hub_flag.p, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,

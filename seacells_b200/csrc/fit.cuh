@@ -49,7 +49,6 @@ struct sc_fit {
   DBuf<double> part_v, cmax_v, bound_v;
   DBuf<int> cmax_l;
   DBuf<unsigned char> hub_flag;
-  int last_hubs = 0;
   DBuf<unsigned long long> eval_cnt;
   long long last_evaluated = 0;
   // CUDA-event timing of the dominant kernel (k_updateB_eval, both rounds of one Frank-Wolfe step), always on

@@ -54,6 +54,15 @@ int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbo
  * Number of queries of the last call that needed the recomputation: */
 int sc_knn_fallback_rows(sc_ctx* ctx);
 
+/* The shortlist stage runs on the tensor cores (tcgen05, 3xTF32 split product) when d <= 63; SC_KNN_FFMA=1 forces the
+ * fp32 FFMA tile kernel instead.  Test probe of that stage: s(i,j) = xi.xj - ||xj||^2/2 as the tensor cores computed it
+ * for the first 128 queries against references [0, cols)  (s_out [128 x cols]), plus the mean-centred fp32 embedding
+ * (xc_out [n x d]) and its squared norms (norm2_out [n]) the products were formed from; host buffers.
+ * sc_knn_tc_error_factor(d) is the certificate's bound on |(||xi||^2 - 2 s) - ||xi-xj||^2| / (||xi|| + ||xj||)^2. */
+int sc_knn_tc_probe(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int cols, float* s_out, float* xc_out,
+                    float* norm2_out);
+double sc_knn_tc_error_factor(int d);
+
 /* SEACellGraph.rbf(k, graph_construction) (build_graph.py:113): kNN, sigma (18-34), union/intersection (155-164),
  * Gaussian values (37-61), CSR (181-188).  intersection: 0 = "union", 1 = "intersect"/"intersection". */
 int sc_kernel_build(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int intersection,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "sc_stream": (_vp, [_vp]),
     "sc_version": (C.c_char_p, []),
     "sc_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sc_knn_tc_probe": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sc_knn_tc_error_factor": (_d, [_i]),
     "sc_kernel_build": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _pp, C.POINTER(_ll)]),
     "sc_kernel_build_from_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _pp, C.POINTER(_ll)]),
     "sc_kernel_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -151,6 +151,29 @@ int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbo
   return SC_OK;
 }
 
+int sc_knn_tc_probe(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int cols, float* s_out, float* xc_out,
+                    float* norm2_out) {
+  if (!ctx || !X || !s_out || !xc_out || !norm2_out || n <= 0 || d <= 0 || cols <= 0) return SC_ERR_ARG;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t esz = x_is_f64 ? 8 : 4;
+  DBuf<char> xs;
+  const char* Xd = nullptr;
+  SC_TRY(to_device<char>(ctx, (const char*)X, (size_t)n * d * esz, xs, &Xd));
+  DBuf<float> s, xc, nn;
+  SC_TRY(s.ensure(ctx, (size_t)128 * cols));
+  SC_TRY(xc.ensure(ctx, (size_t)n * d));
+  SC_TRY(nn.ensure(ctx, (size_t)n));
+  SC_CUDA(ctx, cudaMemsetAsync(s.p, 0, sizeof(float) * 128 * (size_t)cols, ctx->stream));
+  SC_TRY(sc_knn_tc_probe_dev(ctx, Xd, x_is_f64, n, d, cols, s.p, xc.p, nn.p));
+  SC_CUDA(ctx, sc_copy(s_out, s.p, sizeof(float) * 128 * (size_t)cols, ctx->stream));
+  SC_CUDA(ctx, sc_copy(xc_out, xc.p, sizeof(float) * (size_t)n * d, ctx->stream));
+  SC_CUDA(ctx, sc_copy(norm2_out, nn.p, sizeof(float) * (size_t)n, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SC_OK;
+}
+
+double sc_knn_tc_error_factor(int d) { return sc_knn_tc_gamma(d); }
+
 static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors,
                              const int32_t* idx, const double* d2, int intersection, sc_kernel** out,
                              long long* nnz_out) {

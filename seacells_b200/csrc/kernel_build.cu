@@ -388,13 +388,20 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
   SC_LAUNCH(ctx, k_col_mean, d, 256, 0, X, x_is_f64, n, d, mean.p);
   SC_LAUNCH(ctx, k_center, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, X, x_is_f64, n, d, mean.p, Xc.p, norm2.p,
             maxnorm.p);
-  const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(float) + (size_t)KNN_QT * (KNN_RT + 1) * sizeof(float) +
-                      KNN_RT * sizeof(float);
-  SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SC_LAUNCH(ctx, k_knn_filter, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, Xc.p, norm2.p, n, d, row_begin, row_end,
-            cand.p, thr.p);
-  // error bound of the fp32 pipeline (conversion, norms, d-term dot product, final combination), 4x conservative
-  const double gamma = (double)(d + 8) * 4.0 * 5.9604644775390625e-08;
+  double gamma;
+  if (sc_knn_tc_supported(n, d) && getenv("SC_KNN_FFMA") == nullptr) {
+    // tensor-core filter (knn_tc.cu): 3xTF32 split product, fp32 accumulation in tensor memory
+    SC_TRY(sc_knn_filter_tc(ctx, Xc.p, norm2.p, n, d, row_begin, row_end, cand.p, thr.p, nullptr, 0));
+    gamma = sc_knn_tc_gamma(d);
+  } else {
+    const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(float) +
+                        (size_t)KNN_QT * (KNN_RT + 1) * sizeof(float) + KNN_RT * sizeof(float);
+    SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SC_LAUNCH(ctx, k_knn_filter, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, Xc.p, norm2.p, n, d, row_begin,
+              row_end, cand.p, thr.p);
+    // error bound of the fp32 pipeline (conversion, norms, d-term dot product, final combination), 4x conservative
+    gamma = (double)(d + 8) * 4.0 * 5.9604644775390625e-08;
+  }
   if (x_is_f64) {
     SC_LAUNCH(ctx, k_knn_rerank<double>, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, (const double*)X, norm2.p,
               maxnorm.p, n, d, kk, row_begin, row_end, cand.p, thr.p, gamma, idx, d2, fail.p, fail.p + rows);
@@ -411,6 +418,27 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
     else SC_TRY(launch_knn<float>(ctx, (const float*)X, n, d, kk, 0, nfail, fail.p, row_begin, idx, d2));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  return SC_OK;
+}
+
+// Test probe: centre X, run the tensor-core filter on the first 128 queries and return the raw s(i,j) tile together
+// with the centred fp32 embedding and the fp32 norms it was computed from (all device buffers).
+int sc_knn_tc_probe_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int cols, float* s_out, float* xc_out,
+                        float* norm2_out) {
+  if (!sc_knn_tc_supported(n, d)) SC_FAIL(ctx, SC_ERR_ARG, "knn tensor-core probe: unsupported shape");
+  DBuf<double> mean;
+  DBuf<float> maxnorm, thr;
+  DBuf<int> cand;
+  const int rows = n < 128 ? n : 128;
+  SC_TRY(mean.ensure(ctx, (size_t)d));
+  SC_TRY(maxnorm.ensure(ctx, 4));
+  SC_TRY(thr.ensure(ctx, (size_t)rows));
+  SC_TRY(cand.ensure(ctx, (size_t)rows * KF_NC));
+  SC_CUDA(ctx, cudaMemsetAsync(maxnorm.p, 0, sizeof(float) * 4, ctx->stream));
+  SC_LAUNCH(ctx, k_col_mean, d, 256, 0, X, x_is_f64, n, d, mean.p);
+  SC_LAUNCH(ctx, k_center, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, X, x_is_f64, n, d, mean.p, xc_out,
+            norm2_out, maxnorm.p);
+  SC_TRY(sc_knn_filter_tc(ctx, xc_out, norm2_out, n, d, 0, rows, cand.p, thr.p, s_out, cols));
   return SC_OK;
 }
 

@@ -317,7 +317,7 @@ __global__ void k_knn_rerank(const TX* __restrict__ X, const float* __restrict__
   if (gq >= row_end) return;
   int j = cand_idx[(size_t)warp * KF_NC + lane];
   double dd = INFINITY;
-  if (j != 0x7fffffff) {
+  if (j != 0x7fffffff && j != gq) {  // the tensor-core filter leaves the query itself in its shortlist
     const TX* __restrict__ xi = X + (size_t)gq * d;
     const TX* __restrict__ xj = X + (size_t)j * d;
     double acc = 0.0;

@@ -10,21 +10,26 @@
 // extra K column (A holds 1 there), so the epilogue is a pure "is anything in this row chunk above my threshold" scan.
 //
 // Layout
-//   operands   pre-tiled in global memory (k_knn_pack): one block of KP*1024 bytes per 128 cells = hi part + lo part,
+//   references pre-tiled in global memory (k_knn_pack): one block of KP*1024 bytes per 128 cells = hi part + lo part,
 //              each already in the shared-memory image tcgen05.mma wants (K-major, no swizzle: 8x16-byte core
 //              matrices, row groups 128 B apart (SBO), K chunks 2048 B apart (LBO)); KP = round_up(d+1, 8).
 //   CTA        persistent, one per SM, 256 threads: warp 0 = bulk-copy producer (cp.async.bulk -> UBLKCP),
 //              warp 1 = MMA issuer (one thread; tcgen05.mma kind::tf32, M=128 N=128 K=8), warps 4-7 = epilogue
-//              (tcgen05.ld 32x32b: one query row per thread).  A query tile (128 rows) stays in shared memory while
-//              all reference tiles stream through a 2-stage ring; accumulators are double buffered in TMEM
-//              (2 x 128 columns) so the MMAs of tile t+1 run under the scan of tile t.
+//              (tcgen05.ld 32x32b: one query row per thread).  The query tile (128 rows, hi and lo) lives in TENSOR
+//              MEMORY (written once per query tile by the epilogue threads with tcgen05.st, A operand of the MMAs):
+//              with both operands in shared memory the MMAs were bound by shared-memory bandwidth (8 KB of operand
+//              reads per 64-cycle MMA next to the bulk copies: 95 cycles per MMA measured).  Reference tiles stream
+//              through a 3-stage ring; accumulators are triple buffered in TMEM (3 x 128 columns) so the MMAs of the
+//              next tiles run under the scan of this one.  TMEM map: [0,384) accumulators, [384,448) A hi, [448,512) A lo.
 //   selection  per row: threshold register + append buffer (128 entries, L2-resident scratch); a row whose buffer
-//              passes 96 entries is compacted to its best 32 by the whole warp (rank counting over shuffles).
+//              passes 96 entries is compacted to its best 32 by the whole warp (bitwise radix select over votes).
+//              The query itself is not excluded here (it is simply the best candidate): k_knn_rerank drops it.
 //
 // Every mbarrier wait is bounded (2 s): a broken pipeline sets an error flag and drains instead of hanging the GPU.
 #include "kernel_build.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -34,7 +39,9 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_CAP = 128;        // append-buffer entries per row
 constexpr int TC_TRIG = 96;        // compact when a row holds more than this after a chunk
 constexpr int TC_KEEP = 32;        // shortlist size (== KF_NC in kernel_build.cu)
-constexpr int TC_TMEM_COLS = 256;  // 2 accumulator buffers x 128 fp32 columns
+constexpr int TC_TMEM_COLS = 512;  // 3 accumulator buffers x 128 fp32 columns + the query tile (hi, lo: 64 columns each)
+constexpr int TC_STAGES = 3;
+constexpr uint32_t TC_COL_AHI = 384, TC_COL_ALO = 448;
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,12 +68,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait: false (and the shared abort flag set) when the barrier did not flip within ~2 s
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (true) {
-    if (mbar_try_wait(bar, parity)) return true;
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin)
+      if (mbar_try_wait(bar, parity)) return true;
     if (*abort_flag) return false;
     if (clock64() - t0 > 4000000000ll) {
       *abort_flag = 1;
@@ -84,17 +106,24 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// A operand from tensor memory (lane = row, column = k), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -124,47 +153,44 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
-// (s, reference) -> 64-bit key: larger key = better candidate (larger s, then smaller reference index)
-__device__ __forceinline__ unsigned long long cand_key(float s, int idx) {
-  uint32_t u = __float_as_uint(s);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return ((unsigned long long)u << 32) | (uint32_t)(~(uint32_t)idx);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0;
 }
+
+// order-preserving map of fp32 bit patterns onto unsigned integers, and its inverse
+__device__ __forceinline__ uint32_t ordered_bits(uint32_t f) { return (f & 0x80000000u) ? ~f : (f | 0x80000000u); }
+__device__ __forceinline__ uint32_t unordered_bits(uint32_t u) { return (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; }
 
 }  // namespace
 
 // ---- operand packing --------------------------------------------------------------------------------------------
-// One 16-byte unit (4 consecutive K columns of one cell) per thread, for the hi and the lo part.
-// is_query: extra column = 1, padding rows all zero.   reference: extra column = -||x||^2/2, padding rows -1e30 there.
+// Reference tiles: one 16-byte unit (4 consecutive K columns of one cell) per thread, for the hi and the lo part.
+// Column d holds -||x||^2/2; rows past n get -1e30 there (never shortlisted) and zeros elsewhere.
 __global__ void k_knn_pack(const float* __restrict__ Xc, const float* __restrict__ norm2, int n, int d, int KP,
-                           int row_begin, int row_end, int is_query, float4* __restrict__ out) {
+                           float4* __restrict__ out) {
   const int KC = KP >> 2;
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int rows = row_end - row_begin;
-  const long long n_tiles = (rows + TC_M - 1) / TC_M;
+  const long long n_tiles = (n + TC_N - 1) / TC_N;
   if (u >= n_tiles * KC * 128) return;
   const long long tile = u / (KC * 128);
   const int w = (int)(u - tile * (KC * 128));
   const int kc = w >> 7, r = w & 127;
-  const long long cell = (long long)row_begin + tile * 128 + r;
-  float x[4];
+  const long long cell = tile * 128 + r;
+  float hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int c = kc * 4 + e;
     float v = 0.f;
-    if (cell < row_end) {
+    if (cell < n) {
       if (c < d) v = Xc[cell * d + c];
-      else if (c == d) v = is_query ? 1.f : -0.5f * norm2[cell];
-    } else if (!is_query && c == d) {
+      else if (c == d) v = -0.5f * norm2[cell];
+    } else if (c == d) {
       v = -1e30f;
     }
-    x[e] = v;
-  }
-  float hi[4], lo[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    hi[e] = tf32_rna(x[e]);
-    lo[e] = tf32_rna(x[e] - hi[e]);
+    hi[e] = tf32_rna(v);
+    lo[e] = tf32_rna(v - hi[e]);
   }
   float4* tb = out + tile * (size_t)(2 * KC * 128);
   tb[w] = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -172,8 +198,11 @@ __global__ void k_knn_pack(const float* __restrict__ Xc, const float* __restrict
 }
 
 // ---- the filter -------------------------------------------------------------------------------------------------
+#define TC_TRACE(ev) do { if (a.trace && blockIdx.x == 0 && qcount == 0 && rt >= a.trace_off && rt < a.trace_off + 256) a.trace[(rt - a.trace_off) * 8 + (ev)] = clock64(); } while (0)
+
 struct TcArgs {
-  const unsigned char* TA;   // packed query tiles of [row_begin, row_end)
+  const float* Xc;           // centred embedding [n x d] (the query tile is split and written to TMEM in-kernel)
+  int d;
   const unsigned char* TB;   // packed reference tiles of all n cells
   const float* norm2;
   int n, KP, row_begin, row_end, n_q_tiles, n_r_tiles;
@@ -183,47 +212,70 @@ struct TcArgs {
   int* err;
   float* dbg_s;              // optional [128 x dbg_cols]: raw s of query tile 0
   int dbg_cols;
+  int trace_off;
+  long long* trace;          // development: clock64 stamps of CTA 0, [256 tiles x 8 events]
 };
 
-// warp-cooperative compaction of one row buffer to its best TC_KEEP entries (sorted, best first); returns the
-// TC_KEEP-th best s (or -inf when the row holds fewer)
+// warp-cooperative compaction of one row buffer (c > TC_KEEP entries) to its best TC_KEEP entries, written to
+// rowbuf[0..TC_KEEP) in no particular order; returns the TC_KEEP-th largest s.  Exact selection by a bitwise radix
+// descent on the order-preserving 32-bit image of s: one vote per key register and bit, no sorting.
 __device__ __forceinline__ float compact_row(unsigned long long* __restrict__ rowbuf, int c, int lane) {
-  unsigned long long key[TC_CAP / 32];
+  constexpr int R = TC_CAP / 32;
+  uint32_t u[R], x[R];
+  bool valid[R];
 #pragma unroll
-  for (int i = 0; i < TC_CAP / 32; ++i) {
+  for (int i = 0; i < R; ++i) {
     const int e = i * 32 + lane;
-    key[i] = (e < c) ? rowbuf[e] : 0ull;
+    valid[i] = e < c;
+    const uint2 k = valid[i] ? reinterpret_cast<const uint2*>(rowbuf)[e] : make_uint2(0u, 0u);
+    u[i] = valid[i] ? ordered_bits(k.y) : 0u;  // order-preserving image of s
+    x[i] = k.x;                                // reference index
   }
   __syncwarp();
-  int rank[TC_CAP / 32];
+  // bits above the highest bit in which two valid keys differ are common to all of them
+  uint32_t v_or = 0u, v_and = 0xffffffffu;
 #pragma unroll
-  for (int i = 0; i < TC_CAP / 32; ++i) rank[i] = 0;
+  for (int i = 0; i < R; ++i)
+    if (valid[i]) {
+      v_or |= u[i];
+      v_and &= u[i];
+    }
+  v_or = __reduce_or_sync(FULLMASK, v_or);
+  v_and = __reduce_and_sync(FULLMASK, v_and);
+  const uint32_t diff = v_or ^ v_and;
+  uint32_t prefix = v_and;
+  if (diff != 0u) {
+    const int hb = 31 - __clz(diff);
+    prefix = (hb == 31) ? 0u : (v_and & ~((2u << hb) - 1u));
+    for (int bit = hb; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int n_ge = 0;
 #pragma unroll
-  for (int i2 = 0; i2 < TC_CAP / 32; ++i2) {
-    if (i2 * 32 < c) {
-      const int lim = min(32, c - i2 * 32);
-      for (int jj = 0; jj < lim; ++jj) {
-        const unsigned long long kj = __shfl_sync(FULLMASK, key[i2], jj);
-#pragma unroll
-        for (int i = 0; i < TC_CAP / 32; ++i) rank[i] += (kj > key[i]) ? 1 : 0;
-      }
+      for (int i = 0; i < R; ++i) n_ge += __popc(__ballot_sync(FULLMASK, valid[i] && u[i] >= cand));
+      if (n_ge >= TC_KEEP) prefix = cand;
     }
   }
-  unsigned long long k32 = 0ull;
+  // prefix == TC_KEEP-th largest value: keep everything above it, and as many ties as are needed to reach TC_KEEP
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int n_gt = 0;
 #pragma unroll
-  for (int i = 0; i < TC_CAP / 32; ++i) {
-    const int e = i * 32 + lane;
-    if (e < c && rank[i] < TC_KEEP) rowbuf[rank[i]] = key[i];
-    if (e < c && rank[i] == TC_KEEP - 1) k32 = key[i];
+  for (int i = 0; i < R; ++i) n_gt += __popc(__ballot_sync(FULLMASK, valid[i] && u[i] > prefix));
+  int base_gt = 0, base_eq = n_gt;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const bool gt = valid[i] && u[i] > prefix, eq = valid[i] && u[i] == prefix;
+    const unsigned bg = __ballot_sync(FULLMASK, gt), be = __ballot_sync(FULLMASK, eq);
+    const uint2 k = make_uint2(x[i], unordered_bits(u[i]));
+    if (gt) reinterpret_cast<uint2*>(rowbuf)[base_gt + __popc(bg & lt_mask)] = k;
+    if (eq) {
+      const int pos = base_eq + __popc(be & lt_mask);
+      if (pos < TC_KEEP) reinterpret_cast<uint2*>(rowbuf)[pos] = k;
+    }
+    base_gt += __popc(bg);
+    base_eq += __popc(be);
   }
-  // exactly one lane (or none) holds the TC_KEEP-th key
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) k32 |= __shfl_xor_sync(FULLMASK, k32, o);
   __syncwarp();
-  if (k32 == 0ull) return -INFINITY;
-  uint32_t u = (uint32_t)(k32 >> 32);
-  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-  return __uint_as_float(u);
+  return __uint_as_float(unordered_bits(prefix));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
@@ -231,25 +283,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t part_bytes = (uint32_t)a.KP * 512u;  // hi (or lo) part of one 128-row tile
   const uint32_t tile_bytes = 2u * part_bytes;
-  unsigned char* sA = smem;
-  unsigned char* sB = smem + tile_bytes;  // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3u * tile_bytes);
-  // bars[0..1] full, [2..3] empty, [4..5] tmem full, [6..7] tmem empty, [8] A tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  unsigned char* sB = smem;  // TC_STAGES reference-tile stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * tile_bytes);
+  // bars[0..2] full, [3..5] empty, [6..8] tmem full, [9..11] tmem empty, [12] query tile written to TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_FULL = 0, B_EMPTY = 3, B_TFULL = 6, B_TEMPTY = 9, B_A = 12;
 
   if (tid == 0) {
-    mbar_init(BAR(0), 1);
-    mbar_init(BAR(1), 1);
-    mbar_init(BAR(2), 1);
-    mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), 1);
-    mbar_init(BAR(5), 1);
-    mbar_init(BAR(6), 4);
-    mbar_init(BAR(7), 4);
-    mbar_init(BAR(8), 1);
+    for (int b = 0; b < TC_STAGES; ++b) {
+      mbar_init(BAR(B_FULL + b), 1);
+      mbar_init(BAR(B_EMPTY + b), 1);
+      mbar_init(BAR(B_TFULL + b), 1);
+      mbar_init(BAR(B_TEMPTY + b), 4);
+    }
+    mbar_init(BAR(B_A), 4);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -267,128 +317,216 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
   uint32_t it = 0;      // reference-tile iterations done by this CTA (ring / accumulator phase bookkeeping)
   uint32_t qcount = 0;  // query tiles done by this CTA
   for (int qt = blockIdx.x; qt < a.n_q_tiles; qt += gridDim.x, ++qcount) {
+    // ring position of this query tile's first reference tile (stage ring and accumulator ring move together)
+    uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+    auto advance = [&]() {
+      if (++s == TC_STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    };
+    // Producer and MMA warps run their loops warp-uniformly and elect one lane only around the asynchronous
+    // instructions: addresses and descriptors then live in uniform registers.  (Issued from inside an `if (lane == 0)`
+    // region every tcgen05.mma needed five R2UR moves and cost ~95 cycles instead of its 64-cycle floor;
+    // scripts/microbench/mma_rate.cu.)
     if (warp == 0) {
-      // ===== producer: one thread streams the packed tiles with bulk copies =====
-      if (lane == 0) {
-        mbar_expect_tx(BAR(8), tile_bytes);
-        const unsigned char* src = a.TA + (size_t)qt * tile_bytes;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) bulk_g2s(smem_u32(sA) + p * (tile_bytes / 4), src + p * (tile_bytes / 4), tile_bytes / 4, BAR(8));
-        uint32_t i = it;
-        for (int rt = 0; rt < a.n_r_tiles; ++rt, ++i) {
-          const uint32_t s = i & 1u, ph = (i >> 1) & 1u;
-          if (!mbar_wait(BAR(2 + s), ph ^ 1u, abort_flag)) break;
-          mbar_expect_tx(BAR(s), tile_bytes);
+      // ===== producer: streams the packed reference tiles with bulk copies =====
+      const bool leader = elect_one();
+      for (int rt = 0; rt < a.n_r_tiles; ++rt, advance()) {
+        bool ok = mbar_wait(BAR(B_EMPTY + s), ph ^ 1u, abort_flag);
+        ok = __all_sync(FULLMASK, ok);
+        if (!ok) break;
+        if (leader) {
+          TC_TRACE(0);
+          mbar_expect_tx(BAR(B_FULL + s), tile_bytes);
           const unsigned char* srcb = a.TB + (size_t)rt * tile_bytes;
           const uint32_t dst = smem_u32(sB) + s * tile_bytes;
 #pragma unroll
-          for (int p = 0; p < 4; ++p) bulk_g2s(dst + p * (tile_bytes / 4), srcb + p * (tile_bytes / 4), tile_bytes / 4, BAR(s));
+          for (int p = 0; p < 4; ++p)
+            bulk_g2s(dst + p * (tile_bytes / 4), srcb + p * (tile_bytes / 4), tile_bytes / 4, BAR(B_FULL + s));
         }
+        __syncwarp();
       }
-      __syncwarp();
     } else if (warp == 1) {
-      // ===== MMA issuer: one thread, 3 x KP/8 tcgen05.mma per reference tile =====
-      if (lane == 0) {
-        bool ok = mbar_wait(BAR(8), qcount & 1u, abort_flag);
-        const uint64_t dA_hi = make_desc(smem_u32(sA)), dA_lo = make_desc(smem_u32(sA) + part_bytes);
-        const int ksteps = a.KP >> 3;
-        uint32_t i = it;
-        for (int rt = 0; ok && rt < a.n_r_tiles; ++rt, ++i) {
-          const uint32_t s = i & 1u, ph = (i >> 1) & 1u;
-          if (!mbar_wait(BAR(6 + s), ph ^ 1u, abort_flag)) break;  // accumulator buffer drained by the epilogue
-          if (!mbar_wait(BAR(s), ph, abort_flag)) break;            // reference tile landed
-          tc_fence_after();
-          const uint32_t sb = smem_u32(sB) + s * tile_bytes;
-          const uint64_t dB_hi = make_desc(sb), dB_lo = make_desc(sb + part_bytes);
-          const uint32_t dtm = tmem_base + s * (uint32_t)TC_N;
-          // each K step (8 tf32 = 2 chunks of 16 B) advances the start address by 2 * LBO = 4096 B = 256 units
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(dtm, dA_lo + (uint64_t)(k * 256), dB_hi + (uint64_t)(k * 256), TC_IDESC, k > 0);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(dtm, dA_hi + (uint64_t)(k * 256), dB_lo + (uint64_t)(k * 256), TC_IDESC, 1u);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(dtm, dA_hi + (uint64_t)(k * 256), dB_hi + (uint64_t)(k * 256), TC_IDESC, 1u);
-          tc_commit(BAR(2 + s));  // shared-memory stage free once these MMAs have read it
-          tc_commit(BAR(4 + s));  // accumulator ready for the epilogue
+      // ===== MMA issuer: 3 x KP/8 tcgen05.mma per reference tile, issued by one elected lane =====
+      const bool leader = elect_one();
+      bool ok = mbar_wait(BAR(B_A), qcount & 1u, abort_flag);  // query tile is in tensor memory
+      ok = __all_sync(FULLMASK, ok);
+      const uint32_t tA_hi = tmem_base + TC_COL_AHI, tA_lo = tmem_base + TC_COL_ALO;
+      const int ksteps = a.KP >> 3;
+      bool pre_ok = false;  // barriers of this tile were already seen complete while the previous tile was issued
+      for (int rt = 0; ok && rt < a.n_r_tiles; ++rt, advance()) {
+        if (!pre_ok) {
+          ok = mbar_wait(BAR(B_TEMPTY + s), ph ^ 1u, abort_flag);           // accumulator drained by the epilogue
+          if (leader) TC_TRACE(1);
+          ok = ok && mbar_wait(BAR(B_FULL + s), ph, abort_flag);            // reference tile landed
+          if (leader) TC_TRACE(2);
+          ok = __all_sync(FULLMASK, ok);
+          if (!ok) break;
         }
+        tc_fence_after();
+        const uint32_t sb = smem_u32(sB) + s * tile_bytes;
+        const uint64_t dB_hi = make_desc(sb), dB_lo = make_desc(sb + part_bytes);
+        const uint32_t dtm = tmem_base + s * (uint32_t)TC_N;
+        // per K step (8 tf32): A advances 8 TMEM columns, B by 2 chunks = 2 * LBO = 4096 B = 256 descriptor units
+        if (leader) {
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_lo + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, k > 0);
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_lo + (uint64_t)(k * 256), TC_IDESC, 1u);
+        }
+        __syncwarp();
+        // the issue above blocks on the tensor pipe's queue; look at the next tile's barriers now, while the pipe
+        // still has work queued, so that the hand-over between tiles does not drain it
+        pre_ok = false;
+        if (rt + 1 < a.n_r_tiles) {
+          const uint32_t s1 = (s + 1 == TC_STAGES) ? 0u : s + 1u, ph1 = (s + 1 == TC_STAGES) ? (ph ^ 1u) : ph;
+          pre_ok = mbar_test(BAR(B_TEMPTY + s1), ph1 ^ 1u) && mbar_test(BAR(B_FULL + s1), ph1);
+          pre_ok = __all_sync(FULLMASK, pre_ok);
+        }
+        if (leader) {
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, 1u);
+          tc_commit(BAR(B_EMPTY + s));  // shared-memory stage free once these MMAs have read it
+          tc_commit(BAR(B_TFULL + s));  // accumulator ready for the epilogue
+          TC_TRACE(3);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     } else if (warp >= 4) {
       // ===== epilogue: one query row per thread =====
       const int q = warp & 3;
       const int row_in_tile = q * 32 + lane;
-      const long long self_ll = (long long)a.row_begin + (long long)qt * TC_M + row_in_tile;
-      const int self = (int)self_ll;
       unsigned long long* rowbuf = a.scratch + ((size_t)blockIdx.x * TC_M + row_in_tile) * TC_CAP;
       unsigned long long* warpbuf = a.scratch + ((size_t)blockIdx.x * TC_M + q * 32) * TC_CAP;
       float thr = -INFINITY;
       int cnt = 0;
-      uint32_t i = it;
       bool ok = true;
-      for (int rt = 0; rt < a.n_r_tiles; ++rt, ++i) {
-        const uint32_t s = i & 1u, ph = (i >> 1) & 1u;
-        ok = mbar_wait(BAR(4 + s), ph, abort_flag);
-        ok = __all_sync(FULLMASK, ok);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)TC_N;
-#pragma unroll 1
-        for (int ch = 0; ch < TC_N / 32; ++ch) {
-          uint32_t v[32];
-          tc_ld32(tbase + ch * 32, v);
-          tc_wait_ld();
-          const int col0 = rt * TC_N + ch * 32;
-          if (a.dbg_s != nullptr && qt == 0) {
+      {
+        // this thread's query row -> tensor memory: x = hi + lo (tf32 each), extra column d holds 1 (it multiplies
+        // the references' -||xj||^2/2 column), padding columns and rows past row_end are zero
+        const long long grow = (long long)a.row_begin + (long long)qt * TC_M + row_in_tile;
+        const bool live = grow < a.row_end;
+        const float* __restrict__ xr = a.Xc + (size_t)(live ? grow : 0) * a.d;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int k8 = 0; k8 < (a.KP >> 3); ++k8) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < a.dbg_cols) a.dbg_s[(size_t)row_in_tile * a.dbg_cols + col0 + j] = __uint_as_float(v[j]);
+          for (int e = 0; e < 8; ++e) {
+            const int c = k8 * 8 + e;
+            float x = 0.f;
+            if (live) x = (c < a.d) ? xr[c] : (c == a.d ? 1.f : 0.f);
+            const float h = tf32_rna(x);
+            hi[e] = __float_as_uint(h);
+            lo[e] = __float_as_uint(tf32_rna(x - h));
           }
-          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+          tc_st8(trow + TC_COL_AHI + (uint32_t)(k8 * 8), hi);
+          tc_st8(trow + TC_COL_ALO + (uint32_t)(k8 * 8), lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_A));
+      }
+      // one 32-column chunk of this thread's row: the common case (nothing above the threshold in any of the warp's
+      // 32 rows) costs a max tree and one vote
+      auto scan_chunk = [&](const uint32_t (&v)[32], int col0) {
+        if (a.dbg_s != nullptr && qt == 0) {
 #pragma unroll
-          for (int j = 4; j < 32; j += 4) {
-            m0 = fmaxf(m0, __uint_as_float(v[j]));
-            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
-            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
-          }
-          const bool hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr;
-          if (__any_sync(FULLMASK, hit)) {
-            if (hit) {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < a.dbg_cols) a.dbg_s[(size_t)row_in_tile * a.dbg_cols + col0 + j] = __uint_as_float(v[j]);
+        }
+        float g[4];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sv = __uint_as_float(v[j]);
-                const int col = col0 + j;
-                if (sv > thr && col != self) {
-                  rowbuf[cnt] = cand_key(sv, col);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float m01 = fmaxf(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
+          const float m23 = fmaxf(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
+          const float m45 = fmaxf(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
+          const float m67 = fmaxf(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
+          g[q4] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+        }
+        const bool hit = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) > thr;
+        if (__any_sync(FULLMASK, hit)) {
+          // hits are rare: one vote per group of 8 columns, then predicated (branch-free) appends inside a group
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (__any_sync(FULLMASK, g[q4] > thr)) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const uint32_t sb = v[q4 * 8 + jj];
+                if (__uint_as_float(sb) > thr) {
+                  reinterpret_cast<uint2*>(rowbuf)[cnt] = make_uint2((uint32_t)(col0 + q4 * 8 + jj), sb);
                   ++cnt;
                 }
               }
             }
-            __syncwarp();
-            unsigned need = __ballot_sync(FULLMASK, cnt > TC_TRIG);
-            while (need) {
-              const int L = __ffs(need) - 1;
-              need &= need - 1;
-              const int c = __shfl_sync(FULLMASK, cnt, L);
-              const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
-              if (lane == L) {
-                thr = t;
-                cnt = TC_KEEP;
-              }
+          }
+          __syncwarp();
+          unsigned need = __ballot_sync(FULLMASK, cnt > TC_TRIG);
+          while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const int c = __shfl_sync(FULLMASK, cnt, L);
+            const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
+            if (lane == L) {
+              thr = t;
+              cnt = TC_KEEP;
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(6 + s));
+      };
+      for (int rt = 0; rt < a.n_r_tiles; ++rt, advance()) {
+        ok = mbar_wait(BAR(B_TFULL + s), ph, abort_flag);
+        ok = __all_sync(FULLMASK, ok);
+        if (!ok) break;
+        if (warp == 4 && lane == 0) TC_TRACE(4);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)TC_N;
+        const int colt = rt * TC_N;
+        {
+          // software pipeline over the 4 chunks: the tensor-memory load of the next chunk is in flight while this
+          // one is scanned
+          uint32_t va[32], vb[32];
+          tc_ld32(tbase, va);
+          tc_wait_ld();
+          tc_ld32(tbase + 32, vb);
+          scan_chunk(va, colt);
+          tc_wait_ld();
+          tc_ld32(tbase + 64, va);
+          scan_chunk(vb, colt + 32);
+          tc_wait_ld();
+          tc_ld32(tbase + 96, vb);
+          scan_chunk(va, colt + 64);
+          tc_wait_ld();
+          // everything of this accumulator buffer is in registers: hand it back before the last scan
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_TEMPTY + s));
+          scan_chunk(vb, colt + 96);
+        }
+        if (warp == 4 && lane == 0) TC_TRACE(5);
       }
       // final shortlist of the 32 rows of this warp
       __syncwarp();
+      {
+        unsigned need = __ballot_sync(FULLMASK, cnt > TC_KEEP);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          const int c = __shfl_sync(FULLMASK, cnt, L);
+          const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
+          if (lane == L) {
+            thr = t;
+            cnt = TC_KEEP;
+          }
+        }
+      }
+      __syncwarp();
       for (int L = 0; L < 32; ++L) {
         const int c = __shfl_sync(FULLMASK, cnt, L);
-        const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
+        const float t = __shfl_sync(FULLMASK, thr, L);
         const long long grow = (long long)a.row_begin + (long long)qt * TC_M + q * 32 + L;
         if (ok && grow < a.row_end) {
           const size_t orow = (size_t)(grow - a.row_begin);
           int idx = 0x7fffffff;
-          if (lane < min(c, TC_KEEP)) idx = (int)(~(uint32_t)(warpbuf[(size_t)L * TC_CAP + lane] & 0xffffffffull));
+          if (lane < c) idx = (int)reinterpret_cast<const uint2*>(warpbuf)[(size_t)L * TC_CAP + lane].x;
           a.cand_idx[orow * TC_KEEP + lane] = idx;
           if (lane == 0) a.cand_thr[orow] = (c >= TC_KEEP) ? fmaf(-2.f, t, a.norm2[grow]) : INFINITY;
         }
@@ -437,26 +575,20 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, in
   SC_CUDA(ctx, cudaGetDevice(&dev));
   SC_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = n_q_tiles < sms ? n_q_tiles : sms;
-  DBuf<unsigned char> TA, TB;
+  DBuf<unsigned char> TB;
   DBuf<unsigned long long> scratch;
   DBuf<int> err;
-  SC_TRY(TA.ensure(ctx, (size_t)n_q_tiles * tile_bytes));
   SC_TRY(TB.ensure(ctx, (size_t)n_r_tiles * tile_bytes));
   SC_TRY(scratch.ensure(ctx, (size_t)grid * TC_M * TC_CAP));
   SC_TRY(err.ensure(ctx, 4));
   SC_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int) * 4, ctx->stream));
   {
-    const long long units = (long long)n_q_tiles * (KP / 4) * 128;
-    SC_LAUNCH(ctx, k_knn_pack, (unsigned)((units + 255) / 256), 256, 0, Xc, norm2, n, d, KP, row_begin, row_end, 1,
-              reinterpret_cast<float4*>(TA.p));
-  }
-  {
     const long long units = (long long)n_r_tiles * (KP / 4) * 128;
-    SC_LAUNCH(ctx, k_knn_pack, (unsigned)((units + 255) / 256), 256, 0, Xc, norm2, n, d, KP, 0, n, 0,
-              reinterpret_cast<float4*>(TB.p));
+    SC_LAUNCH(ctx, k_knn_pack, (unsigned)((units + 255) / 256), 256, 0, Xc, norm2, n, d, KP, reinterpret_cast<float4*>(TB.p));
   }
   TcArgs a;
-  a.TA = TA.p;
+  a.Xc = Xc;
+  a.d = d;
   a.TB = TB.p;
   a.norm2 = norm2;
   a.n = n;
@@ -471,12 +603,49 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, in
   a.err = err.p;
   a.dbg_s = dbg_s;
   a.dbg_cols = dbg_cols;
-  const size_t smem = 3 * tile_bytes + 128;
+  DBuf<long long> trace;
+  a.trace = nullptr;
+  a.trace_off = 0;
+  if (getenv("SC_KNN_TC_TRACE")) {
+    SC_TRY(trace.ensure(ctx, 256 * 8));
+    SC_CUDA(ctx, cudaMemsetAsync(trace.p, 0, sizeof(long long) * 256 * 8, ctx->stream));
+    a.trace = trace.p;
+    a.trace_off = getenv("SC_KNN_TC_TRACE_OFF") ? atoi(getenv("SC_KNN_TC_TRACE_OFF")) : 0;
+  }
+  const size_t smem = TC_STAGES * tile_bytes + 128;
   SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool timing = getenv("SC_KNN_TC_TIME") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timing) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+  }
   SC_LAUNCH(ctx, k_knn_filter_tc, grid, TC_THREADS, smem, a);
+  if (timing) {
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[seacells_b200] k_knn_filter_tc: %.3f ms (rows %d, n %d, KP %d, grid %d)\n", ms, rows, n, KP, grid);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   int herr = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (a.trace && rows > 4096) {
+    std::vector<long long> h(256 * 8);
+    cudaMemcpy(h.data(), trace.p, sizeof(long long) * 256 * 8, cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("SC_KNN_TC_TRACE"), "w");
+    if (f) {
+      for (int t = 0; t < 256; ++t) {
+        for (int e = 0; e < 8; ++e) fprintf(f, "%lld ", h[t * 8 + e] ? h[t * 8 + e] - h[0] : -1ll);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   if (herr) SC_FAIL(ctx, SC_ERR_CUDA, "knn tensor-core filter: pipeline barrier timed out");
   return SC_OK;
 }

@@ -105,6 +105,45 @@ def test_knn_filter_path_is_exact():
     assert np.array_equal(il, np.load("/tmp/_knn_i.npy")) and np.array_equal(dl, np.load("/tmp/_knn_d.npy"))
 
 
+def test_knn_tensor_core_filter():
+    """tcgen05 shortlist stage (d <= 63): realised error of the 3xTF32 split product against the bound the certificate
+    uses, on benign and on badly scaled data; the FFMA filter (d > 63) and the tensor-core filter both stay exact."""
+    from seacells_b200 import _lib, knn
+    from seacells_b200.synth import synth_embedding
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(17)
+    cases = [synth_embedding(4096, 50, 0), synth_embedding(2048 + 77, 30, 1),
+             (rng.normal(size=(3000, 63)) * np.logspace(-3, 3, 63)).astype(np.float32),
+             (rng.normal(size=(2500, 8)) * 1e-2 + rng.integers(0, 3, size=(2500, 1)) * 300.0).astype(np.float32)]
+    for X in cases:
+        n, d = X.shape
+        cols = n
+        s = np.zeros((128, cols), np.float32)
+        xc = np.zeros((n, d), np.float32)
+        nn = np.zeros(n, np.float32)
+        ctx.check(ctx.lib.sc_knn_tc_probe(ctx.h, _lib.ptr(X), 0, n, d, cols, _lib.ptr(s), _lib.ptr(xc), _lib.ptr(nn)),
+                  "sc_knn_tc_probe")
+        x64 = xc.astype(np.float64)
+        ref = x64[:128] @ x64.T - 0.5 * nn.astype(np.float64)[None, :]
+        nr = np.sqrt((x64 ** 2).sum(1))
+        rel = 2.0 * np.abs(s - ref) / np.maximum((nr[:128, None] + nr[None, :]) ** 2, 1e-300)
+        bound = ctx.lib.sc_knn_tc_error_factor(d)
+        assert rel.max() < 0.25 * bound, (rel.max(), bound)   # measured: ~0.005 of the bound
+        idx, d2 = knn(X, 15)
+        io, do = O.knn_exact(X, 15)
+        assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    # d > 63: FFMA filter
+    X = rng.normal(size=(3000, 70)).astype(np.float32)
+    idx, d2 = knn(X, 15)
+    io, do = O.knn_exact(X, 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    # query slab (a rank's shard) through the tensor-core filter, not a multiple of the tile
+    X = synth_embedding(5000, 50, 4)
+    io, do = O.knn_exact(X, 15)
+    pi, pd = knn(X, 15, row_begin=1234, row_end=1234 + 1300)
+    assert np.array_equal(pi, io[1234:2534]) and np.array_equal(pd, do[1234:2534])
+
+
 def test_spmm_csr_dense():
     from seacells_b200 import spmm_csr
     rng = np.random.default_rng(0)

@@ -46,6 +46,29 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _knn_roofline(n, d, world, filter_s, kind, kp, fallback_rows):
+    """Tensor-pipe roofline of the kNN shortlist kernel (hot path 1; not part of fit()): the distance contraction of this
+    rank's query slab against all n cells.  algorithmic = 2 n_q n d; executed = 3 split products over the padded K."""
+    if filter_s <= 0 or kind == 0:
+        return None
+    nq = (n + world - 1) // world
+    alg = 2.0 * nq * n * d / filter_s / 1e12
+    out = {"kernel": {1: "k_knn_filter (fp32 FFMA tiles)", 2: "k_knn_filter_tc (tcgen05 kind::tf32, 3xTF32 split)"}[kind],
+           "filter_ms": filter_s * 1e3, "queries": nq, "algorithmic_tflops": alg, "fallback_rows": fallback_rows}
+    if kind == 2:
+        ex = 3.0 * 2.0 * nq * n * kp / filter_s / 1e12
+        peak, src = 1375.4 / 2, "fallback"
+        p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(p):
+            try:
+                peak, src = float(json.load(open(p))["bf16_tflops_sustained"]) / 2, "measured bf16_tflops_sustained / 2"
+            except Exception:
+                pass
+        out.update({"bound": "tensor", "executed_tf32_tflops": ex, "peak": peak, "unit": "TFLOP/s", "frac": ex / peak,
+                    "peak_source": src + " (TF32 runs at half the bf16 rate; the kernel holds the 1 kW power cap)"})
+    return out
+
+
 def _traffic(n, world):
     """DRAM bytes per launch group from the committed ncu --set full capture (1M cells, 1 GPU only)."""
     p = os.path.join(ROOT, "profiles", "r1_updB_group_traffic.json")
@@ -180,6 +203,10 @@ def run_ours(args):
     km = build_kernel(X, 15, "union", ctx, knn_graph=knn_graph)
     ctx.sync()
     t_build = time.perf_counter() - t0
+    import ctypes as C
+    kp4 = (C.c_double * 4)()
+    ctx.lib.sc_knn_profile(ctx.h, kp4)
+    knn_info = _knn_roofline(n, args.pcs, world, kp4[0] / 1e3, int(kp4[1]), int(kp4[2]), int(kp4[3]))
     M, _, _, _ = km.export(want_knn=False)
     km.close()
     # pinned host buffers: these are what every timed step copies to the device
@@ -283,7 +310,7 @@ def run_ours(args):
                                    f"cells row-sharded over {world} GPUs; per outer iteration one all-gather of the "
                                    "compressed A and 50 all-gathers of k x 4 fp64 argmin partials (NCCL)")},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "knn": knn_info,
            "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": f"full fit() ({cpu_iters} outer iterations) of the oracle restatement of "
                                       f"cpu.SEACellsCPU on a {cpu_n}-cell x 50-PC sample (k={cpu_k}); scipy sparse, "

@@ -53,6 +53,9 @@ int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbo
  * all-fp64 kernel (results are bit-identical either way; SC_KNN_EXACT=1 in the environment forces the all-fp64 kernel).
  * Number of queries of the last call that needed the recomputation: */
 int sc_knn_fallback_rows(sc_ctx* ctx);
+/* Shortlist stage of the last sc_knn / sc_kernel_build call: out4 = { device milliseconds of the shortlist kernel (CUDA
+ * events), kind (0 none, 1 fp32 FFMA tiles, 2 tcgen05 3xTF32), padded K of the tensor-core tiles, fallback rows }. */
+int sc_knn_profile(sc_ctx* ctx, double* out4);
 
 /* The shortlist stage runs on the tensor cores (tcgen05, 3xTF32 split product) when d <= 63; SC_KNN_FFMA=1 forces the
  * fp32 FFMA tile kernel instead.  Test probe of that stage: s(i,j) = xi.xj - ||xj||^2/2 as the tensor cores computed it

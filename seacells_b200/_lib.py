@@ -28,6 +28,7 @@ SIGNATURES = {
     "sc_last_error": (C.c_char_p, [_vp]),
     "sc_launch_count": (C.c_ulonglong, [_vp]),
     "sc_knn_fallback_rows": (_i, [_vp]),
+    "sc_knn_profile": (_i, [_vp, _vp]),
     "sc_sync": (_i, [_vp]),
     "sc_stream": (_vp, [_vp]),
     "sc_version": (C.c_char_p, []),

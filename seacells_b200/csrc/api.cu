@@ -113,6 +113,14 @@ void sc_ctx_destroy(sc_ctx* ctx) {
 const char* sc_last_error(sc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 unsigned long long sc_launch_count(sc_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 int sc_knn_fallback_rows(sc_ctx* ctx) { return ctx ? ctx->last_knn_fallback : 0; }
+int sc_knn_profile(sc_ctx* ctx, double* out4) {
+  if (!ctx || !out4) return SC_ERR_ARG;
+  out4[0] = (double)ctx->last_knn_filter_ms;
+  out4[1] = (double)ctx->last_knn_filter_kind;
+  out4[2] = (double)ctx->last_knn_kp;
+  out4[3] = (double)ctx->last_knn_fallback;
+  return SC_OK;
+}
 void* sc_stream(sc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int sc_sync(sc_ctx* ctx) {

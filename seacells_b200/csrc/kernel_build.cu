@@ -369,6 +369,8 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
   const int rows = row_end - row_begin;
   if (rows == 0) return SC_OK;
   const bool use_filter = n >= 2048 && kk <= 24 && n > KF_NC + 1 && getenv("SC_KNN_EXACT") == nullptr;
+  ctx->last_knn_filter_ms = 0.f;
+  ctx->last_knn_filter_kind = 0;
   if (!use_filter) {
     if (x_is_f64) return launch_knn<double>(ctx, (const double*)X, n, d, kk, row_begin, row_end, nullptr, row_begin, idx, d2);
     return launch_knn<float>(ctx, (const float*)X, n, d, kk, row_begin, row_end, nullptr, row_begin, idx, d2);
@@ -397,8 +399,18 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
     const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(float) +
                         (size_t)KNN_QT * (KNN_RT + 1) * sizeof(float) + KNN_RT * sizeof(float);
     SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    SC_CUDA(ctx, cudaEventCreate(&e0));
+    SC_CUDA(ctx, cudaEventCreate(&e1));
+    SC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     SC_LAUNCH(ctx, k_knn_filter, (rows + KNN_QT - 1) / KNN_QT, KNN_THREADS, smem, Xc.p, norm2.p, n, d, row_begin,
               row_end, cand.p, thr.p);
+    SC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    SC_CUDA(ctx, cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ctx->last_knn_filter_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->last_knn_filter_kind = 1;
     // error bound of the fp32 pipeline (conversion, norms, d-term dot product, final combination), 4x conservative
     gamma = (double)(d + 8) * 4.0 * 5.9604644775390625e-08;
   }

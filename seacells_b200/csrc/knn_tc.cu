@@ -614,23 +614,22 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, in
   }
   const size_t smem = TC_STAGES * tile_bytes + 128;
   SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const bool timing = getenv("SC_KNN_TC_TIME") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (timing) {
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, ctx->stream);
-  }
+  SC_CUDA(ctx, cudaEventCreate(&e0));
+  SC_CUDA(ctx, cudaEventCreate(&e1));
+  SC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   SC_LAUNCH(ctx, k_knn_filter_tc, grid, TC_THREADS, smem, a);
-  if (timing) {
-    cudaEventRecord(e1, ctx->stream);
-    cudaEventSynchronize(e1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+  SC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  SC_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->last_knn_filter_ms = ms;
+  ctx->last_knn_filter_kind = 2;
+  ctx->last_knn_kp = KP;
+  if (getenv("SC_KNN_TC_TIME"))
     fprintf(stderr, "[seacells_b200] k_knn_filter_tc: %.3f ms (rows %d, n %d, KP %d, grid %d)\n", ms, rows, n, KP, grid);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  }
   int herr = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

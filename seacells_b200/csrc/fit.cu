@@ -560,6 +560,7 @@ struct UpdBArgs {
   double* b_val;
   int* b_cnt;
   int* trace;  // [T * k] or null
+  int* amin;   // [k] or null: the cell chosen for every archetype at this step (feeds the incremental K B update)
   unsigned long long* evaluated;  // diagnostics: candidates whose exact gradient was computed
 };
 
@@ -599,9 +600,13 @@ __global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restric
 }
 
 // out[cta][slot][4] = {candidate min G, cell, non-candidate min G, cell} over the CTA's cells
+// incremental = 0: HH[cell, :] = (rows of KB) x T1H, evaluated in full.
+// incremental = 1: KB holds only the step's delta rows K E (see k_kb_merge) and HH the product for the previous B:
+//                  HH <- c_old HH + c_new (delta rows x T1H)  - the same identity as for K B itself, 8x fewer entries.
 __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end, int nh_pad,
                                                      const int* __restrict__ perm, RowLists KB,
                                                      const double* __restrict__ T1H, const double* __restrict__ T2H,
+                                                     double* __restrict__ HH, int incremental, double c_old, double c_new,
                                                      double* __restrict__ out) {
   __shared__ double s_v[8][2][HUB_MAX];
   __shared__ int s_i[8][2][HUB_MAX];
@@ -639,6 +644,13 @@ __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end,
           if (r < R) acc[r] = fma(v, __ldg(trow + r * 32), acc[r]);
       }
     }
+    double* __restrict__ hrow = HH + (size_t)(i - row_begin) * nh_pad + lane;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < R) {
+        if (incremental) acc[r] = __dadd_rn(__dmul_rn(c_old, hrow[r * 32]), __dmul_rn(c_new, acc[r]));
+        hrow[r * 32] = acc[r];
+      }
     const double* __restrict__ t2row = T2H + (size_t)(i - row_begin) * nh_pad + lane;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -1059,7 +1071,83 @@ __global__ void __launch_bounds__(32) k_updateB_step(UpdBArgs g, const double* _
       }
     }
     if (lane == 0 && g.trace) g.trace[(size_t)g.t * k + a] = amin;
+    if (lane == 0 && g.amin) g.amin[a] = amin;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ incremental K B
+// Inside one _updateB call the simplex step is B <- (1 - gamma) B + gamma E with the same gamma for every column and one
+// unit entry per column of E (the chosen cells), so  K B_{t+1} = (1 - gamma) K B_t + gamma K E_t  and K E_t = M (M E_t)
+// is a product with k non-zeros on the right instead of nnz(B) (60x less work at 1M cells).  The reference re-evaluates
+// K @ B from scratch (cpu.py:486); the identity is exact, only the rounding of the fp64 values differs (~1e-15
+// relative), which matters solely through the argmin - SC_FIT_FRESH_KB=1 restores the re-evaluation for comparison.
+__global__ void k_emit_e_pairs(int k, const int* __restrict__ amin, unsigned long long* __restrict__ keys,
+                               double* __restrict__ ones) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= k) return;
+  keys[a] = ((unsigned long long)(unsigned)amin[a] << 32) | (unsigned)a;
+  ones[a] = 1.0;
+}
+
+__global__ void k_merge_len(int n, const int* __restrict__ la, const int* __restrict__ lb, long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  out[i] = (i < n) ? (long long)la[i] + (long long)lb[i] : 0ll;
+}
+
+// New[i,:] = c_old * Old[i,:] (+) c_new * D[i,:] for rows [r0, r1), one warp per row.  Entries of Old keep their order,
+// keys that are new to the row are appended in D's order (both orders are fixed => bitwise reproducible).
+__global__ void __launch_bounds__(256)
+k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict__ new_ptr, int* __restrict__ new_len,
+           int* __restrict__ new_key, double* __restrict__ new_val, double c_old, double c_new) {
+  const int lane = threadIdx.x & 31;
+  const int i = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= r1) return;
+  const int lo = Old.len[i], ld = D.len[i];
+  const long long po = Old.ptr[i], pd = D.ptr[i], pn = new_ptr[i];
+  // old entries, scaled, plus the matching delta entry if there is one
+  for (int ob = 0; ob < lo; ob += 32) {
+    const bool ov = ob + lane < lo;
+    const int ok = ov ? Old.key[po + ob + lane] : -2;
+    double val = ov ? __dmul_rn(c_old, Old.val[po + ob + lane]) : 0.0;
+    for (int db = 0; db < ld; db += 32) {
+      const bool dvd = db + lane < ld;
+      const int dk = dvd ? D.key[pd + db + lane] : -1;
+      const double dv = dvd ? D.val[pd + db + lane] : 0.0;
+      const int cnt = min(32, ld - db);
+      for (int j = 0; j < cnt; ++j) {
+        const int kj = __shfl_sync(0xffffffffu, dk, j);
+        const double vj = __shfl_sync(0xffffffffu, dv, j);
+        if (ok == kj) val = __dadd_rn(val, __dmul_rn(c_new, vj));
+      }
+    }
+    if (ov) {
+      new_key[pn + ob + lane] = ok;
+      new_val[pn + ob + lane] = val;
+    }
+  }
+  // delta entries whose key is new to the row
+  int napp = 0;
+  for (int db = 0; db < ld; db += 32) {
+    const bool dvd = db + lane < ld;
+    const int dk = dvd ? D.key[pd + db + lane] : -1;
+    const double dv = dvd ? D.val[pd + db + lane] : 0.0;
+    bool matched = false;
+    for (int ob = 0; ob < lo; ob += 32) {
+      const int ok = (ob + lane < lo) ? Old.key[po + ob + lane] : -2;
+      const int cnt = min(32, lo - ob);
+      for (int j = 0; j < cnt; ++j) matched |= (__shfl_sync(0xffffffffu, ok, j) == dk);
+    }
+    const bool app = dvd && !matched;
+    const unsigned ball = __ballot_sync(0xffffffffu, app);
+    if (app) {
+      const int pos = lo + napp + __popc(ball & ((1u << lane) - 1u));
+      new_key[pn + pos] = dk;
+      new_val[pn + pos] = __dmul_rn(c_new, dv);
+    }
+    napp += __popc(ball);
+  }
+  if (lane == 0) new_len[i] = lo + napp;
 }
 
 // ------------------------------------------------------------------------------------------------ RSS, labels
@@ -1186,6 +1274,7 @@ sc_fit::~sc_fit() {
 int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
   profile = std::getenv("SC_PROFILE") != nullptr;
+  fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
   n = n_;
   row_begin = 0;
   row_end = n_;
@@ -1212,6 +1301,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   SC_TRY(slow_cnt.ensure(ctx, 4));
   SC_TRY(cnt_n.ensure(ctx, (size_t)n + 1));
   SC_TRY(cnt_k.ensure(ctx, (size_t)k + 1));
+  SC_TRY(amin_cur.ensure(ctx, (size_t)k + 1));
   SC_TRY(set_smem_attr_once(ctx));
   return SC_OK;
 }
@@ -1333,6 +1423,68 @@ int sc_fit::compute_KB(int r0, int r1, bool sorted) {
   pstop(P_SPGEMM_Y);
   pstart();
   SC_TRY(sc_spgemm_rows(ctx, M, r0, r1, Y.view(), k, KB, sp, sorted));
+  pstop(P_SPGEMM_KB);
+  return SC_OK;
+}
+
+static void swap_lists(RowListsBuf& a, RowListsBuf& b) {
+  std::swap(a.ptr.p, b.ptr.p);
+  std::swap(a.ptr.cap, b.ptr.cap);
+  std::swap(a.len.p, b.len.p);
+  std::swap(a.len.cap, b.len.cap);
+  std::swap(a.key.p, b.key.p);
+  std::swap(a.key.cap, b.key.cap);
+  std::swap(a.val.p, b.val.p);
+  std::swap(a.val.cap, b.val.cap);
+  std::swap(a.rows, b.rows);
+}
+
+// K B_t from K B_{t-1} and the cells chosen at step t-1 (amin_cur, written by k_updateB_step):
+//   K B_t = (1 - gamma_{t-1}) K B_{t-1} + gamma_{t-1} M (M E_{t-1}),   gamma_0 = 1 (B was reset to E_0)
+int sc_fit::advance_KB(int t) {
+  CsrView M{n, m_ptr.p, m_col.p, m_val.p};
+  pstart();
+  SC_TRY(bk_in.ensure(ctx, (size_t)k + 1));
+  SC_TRY(bk_out.ensure(ctx, (size_t)k + 1));
+  SC_TRY(erow.ptr.ensure(ctx, (size_t)n + 1));
+  SC_TRY(erow.len.ensure(ctx, (size_t)n + 1));
+  SC_TRY(erow.key.ensure(ctx, (size_t)k + 1));
+  SC_TRY(erow.val.ensure(ctx, (size_t)k + 1));
+  SC_LAUNCH(ctx, k_emit_e_pairs, (k + 255) / 256, 256, 0, k, amin_cur.p, bk_in.p, erow.val.p);
+  int nbits = 1;
+  while ((1ll << nbits) < n) nbits++;
+  SC_TRY(sc_sort_keys_u64(ctx, bk_in.p, bk_out.p, (size_t)k, 32 + nbits, tmp));
+  const long long span = std::max<long long>(k, (long long)n + 1);
+  SC_LAUNCH(ctx, k_lists_from_sorted, (unsigned)((span + 255) / 256), 256, 0, n, (long long)k, bk_out.p, erow.ptr.p,
+            erow.len.p, erow.key.p);
+  pstop(P_BROW);
+  pstart();
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, erow.view(), k, EY, sp, false));
+  pstop(P_SPGEMM_Y);
+  pstart();
+  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, EY.view(), k, DKB, sp, false));
+  if (t == 1) {
+    swap_lists(KB, DKB);  // gamma_0 = 1
+  } else {
+    const double gamma = 2.0 / ((double)(t - 1) + 2.0);  // fw_gamma(t - 1)
+    SC_TRY(sp.ub.ensure(ctx, (size_t)n + 1));
+    SC_TRY(KB2.ptr.ensure(ctx, (size_t)n + 1));
+    SC_TRY(KB2.len.ensure(ctx, (size_t)n));
+    SC_LAUNCH(ctx, k_merge_len, (n + 256) / 256, 256, 0, n, KB.len.p, DKB.len.p, sp.ub.p);
+    SC_TRY(sc_exclusive_scan_i64(ctx, sp.ub.p, KB2.ptr.p, (size_t)n + 1, sp.tmp));
+    long long total = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&total, KB2.ptr.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaMemsetAsync(KB2.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SC_TRY(KB2.key.ensure(ctx, (size_t)total + 1));
+    SC_TRY(KB2.val.ensure(ctx, (size_t)total + 1));
+    KB2.rows = n;
+    const int rows = row_end - row_begin;
+    if (rows > 0)
+      SC_LAUNCH(ctx, k_kb_merge, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, row_begin, row_end, KB.view(),
+                DKB.view(), KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p, 1.0 - gamma, gamma);
+    swap_lists(KB, KB2);
+  }
   pstop(P_SPGEMM_KB);
   return SC_OK;
 }
@@ -1549,6 +1701,7 @@ int sc_fit::update_B_begin() {
       const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
       SC_TRY(T1H.ensure(ctx, (size_t)k * n_hub_pad));
       SC_TRY(T2H.ensure(ctx, (size_t)nloc * n_hub_pad));
+      SC_TRY(HH.ensure(ctx, (size_t)nloc * n_hub_pad));
       SC_TRY(hub_part.ensure(ctx, (size_t)nctas * n_hub_pad * 4));
       SC_LAUNCH(ctx, k_hub_t1, dim3((k + 255) / 256, n_hub_pad), 256, 0, k, n_hub, n_hub_pad, hub_ids.p, t1B.p, T1H.p);
       SC_CUDA(ctx, cudaMemsetAsync(T2H.p, 0, sizeof(double) * (size_t)nloc * n_hub_pad, ctx->stream));
@@ -1583,8 +1736,10 @@ int sc_fit::update_B_begin() {
 int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_eval outside update_B_begin/end");
   if (t < 0 || t >= T) SC_FAIL(ctx, SC_ERR_ARG, "update_B_eval: bad step");
-  // K B is re-evaluated from the current B at every step (cpu.py:486); only this rank's rows are needed here
-  SC_TRY(compute_KB(row_begin, row_end, false));  // rows are only walked here: first-occurrence order
+  // K B for the current B (cpu.py:486), this rank's rows, first-occurrence order (the rows are only walked here):
+  // evaluated from B at the first step, then advanced by the step's rank-k change (see k_kb_merge)
+  if (t == 0 || fresh_kb) SC_TRY(compute_KB(row_begin, row_end, false));
+  else SC_TRY(advance_KB(t));
   UpdBArgs g;
   g.n = n;
   g.k = k;
@@ -1600,6 +1755,7 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   g.b_val = b_val.p;
   g.b_cnt = b_cnt.p;
   g.trace = nullptr;
+  g.amin = nullptr;
   g.evaluated = eval_cnt.p;
   const long long nchunks = nchunks_cur;
   pstart();
@@ -1622,8 +1778,11 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (n_hub > 0) {
     const int nloc = row_end - row_begin;
     const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
-    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, KB.view(), T1H.p, T2H.p,
-              hub_part.p);
+    // steps 0 and 1 evaluate the product in full (K B from the previous B, then K E_0); later steps advance it
+    const bool inc = !fresh_kb && t >= 2;
+    const double gamma = inc ? 2.0 / ((double)(t - 1) + 2.0) : 0.0;
+    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, inc ? DKB.view() : KB.view(),
+              T1H.p, T2H.p, HH.p, inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p);
     SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
@@ -1650,6 +1809,7 @@ int sc_fit::update_B_step(int t, const double* gathered_dev, int n_ranks, int* t
   g.b_val = b_val.p;
   g.b_cnt = b_cnt.p;
   g.trace = trace_dev;
+  g.amin = amin_cur.p;
   g.evaluated = nullptr;
   SC_LAUNCH(ctx, k_updateB_step, k, 32, 0, g, gathered_dev, n_ranks);
   return SC_OK;

@@ -14,7 +14,7 @@ struct sc_fit {
   DBuf<int> hub_ids, hub_slot, gram_hubof, perm;
   DBuf<unsigned long long> pk_in, pk_out;
   DBuf<double> gram_tiles;
-  DBuf<double> T1H, T2H, hub_part;
+  DBuf<double> T1H, T2H, HH, hub_part;  // HH: (K B t1)[cell, hubs], advanced step by step
   int n_hub = 0, n_hub_pad = 0, last_hub_block = 0;
   DBuf<double> part_out;  // [k][4] per-archetype partial result of one Frank-Wolfe step of _updateB on this rank
   // kernel matrix M
@@ -34,6 +34,10 @@ struct sc_fit {
   DBuf<double> b_val;
   // B by cell, M*B, K*B
   RowListsBuf brow, Y, KB;
+  // incremental K B inside one _updateB call: chosen cells of the last step, E by cell, M E, K E, second K B buffer
+  DBuf<int> amin_cur;
+  RowListsBuf erow, EY, DKB, KB2;
+  bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   DBuf<long long> b_off;
   DBuf<unsigned long long> bk_in, bk_out;
   DBuf<double> bv_in;
@@ -83,6 +87,7 @@ struct sc_fit {
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
   int compute_KB(int r0, int r1, bool sorted);
+  int advance_KB(int t);
   int build_perm();
   int set_shard(int r0, int r1);
   int update_B_begin();

@@ -84,6 +84,16 @@ void sc_kernel_free(sc_kernel* km);
 int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, const int32_t* indices,
                     const double* data, const double* X, double* Y);
 
+/* ---- next row: metacell aggregation  (core.py:121-242 summarize_by_SEACell / summarize_by_soft_SEACell) -------------- */
+/* out[g, :] = sum over the members (cell, weight) of group g, in ascending cell order, of weight * X[cell, :], divided
+ * by divisor[g] when divisor != NULL.  X: cells x genes counts in CSR (int64 indptr [n+1], int32 indices, float32 or
+ * float64 data); members: m (group, cell, weight) triplets in any order; out: dense row-major [n_groups x n_genes] fp64.
+ * Hard assignment (core.py:215-225): one triplet per cell, weight 1, no divisor.  Soft assignment (core.py:158-166):
+ * the thresholded, row-normalised entries of A^T, divisor = their column sums.  Host or device pointers. */
+int sc_summarize(sc_ctx* ctx, int n, int n_genes, const int64_t* indptr, const int32_t* indices, const void* data,
+                 int data_is_f64, long long m, const int32_t* group, const int32_t* cell, const double* weight,
+                 int n_groups, const double* divisor, double* out);
+
 /* ---- next row: greedy initialisation  (cpu.py:342-423 _get_greedy_centers) ---------------------------------------- */
 /* Greedy adaptive column-subset selection on K = M M^T; M as CSR (host or device pointers), centers_out: host int64
  * [n_centers].  Keeps the reference's dense (n_centers x n) fp64 work matrix, so SC_ERR_CAPACITY when that does not fit. */

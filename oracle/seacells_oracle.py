@@ -373,3 +373,39 @@ def greedy_centers(K, n_centers: int) -> np.ndarray:
         omega[j, :] = o
         centers[j] = p
     return centers
+
+
+# ------------------------------------------------------------------------------------------------ metacell summaries
+def sparsify_assignments(A, thresh):
+    """core.py:103-118 on a dense n_cells x n_SEACells array: zero below `thresh`, renormalise every row."""
+    A = np.array(A, dtype=np.float64, copy=True)
+    A[A < thresh] = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = A / A.sum(1, keepdims=True)
+    return A
+
+
+def summarize_hard(data, labels):
+    """core.py:190-230: per SEACell (order of first appearance, core.py:207) the column sums of its cells' rows.
+
+    data: cells x genes (scipy sparse or ndarray); labels: length-n sequence.  Returns (metacells, dense fp64 matrix)."""
+    labels = np.asarray(labels)
+    _, first = np.unique(labels, return_index=True)
+    metacells = labels[np.sort(first)]
+    data = sp.csr_matrix(data)
+    out = np.zeros((len(metacells), data.shape[1]), dtype=np.float64)
+    for r, m in enumerate(metacells):
+        out[r, :] = np.ravel(data[np.nonzero(labels == m)[0]].sum(axis=0))  # core.py:215-225
+    return metacells, out
+
+
+def summarize_soft(data, A, minimum_weight=0.05):
+    """core.py:121-181: expression[ix] = sum_cells w[cell, ix] * data[cell, :] / sum_cells w[cell, ix] with
+    w = sparsify_assignments(A.T, minimum_weight); pseudo-sizes = w.sum(0).  A: n_SEACells x n_cells dense."""
+    W = sparsify_assignments(np.asarray(A).T, minimum_weight)
+    data = sp.csr_matrix(data)
+    expr = []
+    for ix in range(W.shape[1]):
+        cw = W[:, ix]
+        expr.append(data.multiply(cw[:, np.newaxis]).toarray().sum(0) / cw.sum())  # core.py:158-163
+    return np.array(expr), W.sum(0)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sc_kernel_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sc_kernel_free": (None, [_vp]),
     "sc_spmm_csr_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sc_summarize": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp]),
     "sc_greedy_centers": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _vp]),
     "sc_fit_create": (_i, [_vp, _i, _i, _i, _pp]),
     "sc_fit_destroy": (None, [_vp]),

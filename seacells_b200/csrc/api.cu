@@ -6,6 +6,9 @@
 #include "fit.cuh"
 #include "kernel_build.cuh"
 
+int sc_summarize_dev(sc_ctx* ctx, int n, int n_genes, const long long* x_ptr, const int* x_col, const void* x_val,
+                     int val_is_f64, long long m, const int* group, const int* cell, const double* weight, int n_groups,
+                     const double* divisor, double* out);
 int sc_greedy_centers_impl(sc_ctx* ctx, int n, const int* indptr, const int* indices, const double* data, long long nnz,
                            int n_centers, long long* centers_host);
 
@@ -181,6 +184,49 @@ int sc_knn_tc_probe(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int 
 }
 
 double sc_knn_tc_error_factor(int d) { return sc_knn_tc_gamma(d); }
+
+int sc_summarize(sc_ctx* ctx, int n, int n_genes, const int64_t* indptr, const int32_t* indices, const void* data,
+                 int data_is_f64, long long m, const int32_t* group, const int32_t* cell, const double* weight,
+                 int n_groups, const double* divisor, double* out) {
+  if (!ctx || !indptr || !out || n <= 0 || n_genes <= 0 || n_groups <= 0 || m < 0) return SC_ERR_ARG;
+  if (m > 0 && (!group || !cell || !weight || !indices || !data)) return SC_ERR_ARG;
+  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  long long nnz = 0;
+  {
+    // indptr may be on the host or on the device
+    SC_CUDA(ctx, cudaMemcpyAsync(&nnz, indptr + n, sizeof(long long), cudaMemcpyDefault, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  const size_t esz = data_is_f64 ? 8 : 4;
+  DBuf<long long> s_ptr;
+  DBuf<int> s_col, s_grp, s_cell;
+  DBuf<char> s_val;
+  DBuf<double> s_w, s_div, s_out;
+  const long long* d_ptr = nullptr;
+  const int *d_col = nullptr, *d_grp = nullptr, *d_cell = nullptr;
+  const char* d_val = nullptr;
+  const double *d_w = nullptr, *d_div = nullptr;
+  SC_TRY(to_device<long long>(ctx, (const long long*)indptr, (size_t)n + 1, s_ptr, &d_ptr));
+  SC_TRY(to_device<int>(ctx, indices, (size_t)nnz, s_col, &d_col));
+  SC_TRY(to_device<char>(ctx, (const char*)data, (size_t)nnz * esz, s_val, &d_val));
+  SC_TRY(to_device<int>(ctx, group, (size_t)m, s_grp, &d_grp));
+  SC_TRY(to_device<int>(ctx, cell, (size_t)m, s_cell, &d_cell));
+  SC_TRY(to_device<double>(ctx, weight, (size_t)m, s_w, &d_w));
+  if (divisor) SC_TRY(to_device<double>(ctx, divisor, (size_t)n_groups, s_div, &d_div));
+  const bool out_dev = sc_is_device_ptr(out);
+  double* d_out = out;
+  if (!out_dev) {
+    SC_TRY(s_out.ensure(ctx, (size_t)n_groups * n_genes));
+    d_out = s_out.p;
+  }
+  SC_TRY(sc_summarize_dev(ctx, n, n_genes, d_ptr, d_col, d_val, data_is_f64, m, d_grp, d_cell, d_w, n_groups, d_div,
+                          d_out));
+  if (!out_dev) {
+    SC_CUDA(ctx, sc_copy(out, d_out, sizeof(double) * (size_t)n_groups * n_genes, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SC_OK;
+}
 
 static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors,
                              const int32_t* idx, const double* d2, int intersection, sc_kernel** out,

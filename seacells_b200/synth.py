@@ -46,14 +46,21 @@ def synth_assignments(n: int, k: int, seed: int = 2, per_cell: int = 4) -> sp.cs
     return A0
 
 
-class MiniAnnData:
-    """The slice of the AnnData interface the hot path touches.
+class _Raw:
+    def __init__(self, X):
+        self.X = X
 
-    `.obsm` (dict of n x d arrays), `.obsp` (dict), `.obs` (DataFrame), `.obs_names` (Index), `.shape`.
+
+class MiniAnnData:
+    """The slice of the AnnData interface the hot path and the metacell summaries touch.
+
+    `.obsm` (dict of n x d arrays), `.obsp` (dict), `.obs` (DataFrame), `.obs_names` (Index), `.shape`; optionally a
+    cells x genes matrix `.X` with `.var_names`, `.raw.X`, `.layers` and `ad[cells, :]` row selection by name.
     A real anndata.AnnData works in its place; anndata itself is not a dependency.
     """
 
-    def __init__(self, X: np.ndarray, key: str = "X_pca", names=None):
+    def __init__(self, X: np.ndarray, key: str = "X_pca", names=None, counts=None, var_names=None, raw=None,
+                 layers=None):
         n = X.shape[0]
         self.obsm = {key: X}
         self.obsp = {}
@@ -61,6 +68,34 @@ class MiniAnnData:
         self.shape = (n, X.shape[1])
         self.obs_names = pd.Index([f"c{i}" for i in range(n)] if names is None else names)
         self.obs = pd.DataFrame(index=self.obs_names)
+        self.X = counts
+        self.raw = _Raw(raw) if raw is not None else None
+        self.layers = dict(layers or {})
+        n_var = None
+        for m in (counts, raw, *self.layers.values()):
+            if m is not None:
+                n_var = m.shape[1]
+                break
+        if var_names is not None:
+            self.var_names = pd.Index(var_names)
+        elif n_var is not None:
+            self.var_names = pd.Index([f"g{j}" for j in range(n_var)])
+        if n_var is not None:
+            self.shape = (n, n_var)
+
+    def __getitem__(self, key):
+        cells, cols = key
+        if not (isinstance(cols, slice) and cols == slice(None)):
+            raise NotImplementedError("MiniAnnData only supports ad[cells, :]")
+        pos = self.obs_names.get_indexer(pd.Index(cells))
+        key0 = next(iter(self.obsm))
+        sub = MiniAnnData(self.obsm[key0][pos], key0, names=self.obs_names[pos],
+                          counts=None if self.X is None else self.X[pos],
+                          var_names=getattr(self, "var_names", None),
+                          raw=None if self.raw is None else self.raw.X[pos],
+                          layers={k: v[pos] for k, v in self.layers.items()})
+        sub.obs = self.obs.iloc[pos]
+        return sub
 
     @property
     def n_obs(self):

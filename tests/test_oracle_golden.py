@@ -81,3 +81,16 @@ def test_fit_argument_check():
     g = load_golden("rna_n600_k8_sparse")
     with pytest.raises(ValueError):
         O.fit(csr_from(g, "M"), g["archetypes"], csr_from(g, "A0"), max_iter=3, min_iter=10)
+
+
+def test_summaries_match_reference():
+    """oracle summarize_hard / summarize_soft / sparsify_assignments vs the unmodified core.py (core.py:103-242)."""
+    g = load_golden("summarize_n800_k11")
+    counts = csr_from(g, "counts")
+    names, hard = O.summarize_hard(counts, g["labels"])
+    assert list(names) == list(g["hard_names"])                   # order of first appearance
+    assert np.array_equal(hard, g["hard_X"])                      # integer counts: exact
+    assert np.array_equal(O.summarize_hard(counts * 2, g["labels"])[1], g["hard2_X"])
+    assert np.array_equal(O.sparsify_assignments(g["A"].T, 0.05), g["sparsified"])
+    soft, sizes = O.summarize_soft(counts, g["A"], 0.05)
+    assert np.array_equal(soft, g["soft_X"]) and np.array_equal(sizes, g["soft_sizes"])

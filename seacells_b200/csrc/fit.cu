@@ -1105,6 +1105,38 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
   if (i >= r1) return;
   const int lo = Old.len[i], ld = D.len[i];
   const long long po = Old.ptr[i], pd = D.ptr[i], pn = new_ptr[i];
+  if (ld <= 32) {
+    // common case: the delta row fits one batch - one pass over the old row
+    const bool dvd = lane < ld;
+    const int dk = dvd ? D.key[pd + lane] : -1;
+    const double dv = dvd ? D.val[pd + lane] : 0.0;
+    bool matched = false;
+    for (int ob = 0; ob < lo; ob += 32) {
+      const bool ov = ob + lane < lo;
+      const int ok = ov ? Old.key[po + ob + lane] : -2;
+      double val = ov ? __dmul_rn(c_old, Old.val[po + ob + lane]) : 0.0;
+      for (int j = 0; j < ld; ++j) {
+        const int kj = __shfl_sync(0xffffffffu, dk, j);
+        const double vj = __shfl_sync(0xffffffffu, dv, j);
+        const bool hit = ok == kj;
+        if (hit) val = __dadd_rn(val, __dmul_rn(c_new, vj));
+        if (__any_sync(0xffffffffu, hit) && lane == j) matched = true;
+      }
+      if (ov) {
+        new_key[pn + ob + lane] = ok;
+        new_val[pn + ob + lane] = val;
+      }
+    }
+    const bool app = dvd && !matched;
+    const unsigned ball = __ballot_sync(0xffffffffu, app);
+    if (app) {
+      const int pos = lo + __popc(ball & ((1u << lane) - 1u));
+      new_key[pn + pos] = dk;
+      new_val[pn + pos] = __dmul_rn(c_new, dv);
+    }
+    if (lane == 0) new_len[i] = lo + __popc(ball);
+    return;
+  }
   // old entries, scaled, plus the matching delta entry if there is one
   for (int ob = 0; ob < lo; ob += 32) {
     const bool ov = ob + lane < lo;

@@ -186,6 +186,85 @@ k_spgemm_fill(int row_begin, int row_end, const int* __restrict__ s_ptr, const i
 // are appended in the order they first appear in the (row of S, row of X) sequence - a fixed order - so neither the
 // compaction nor the sort is needed.  The table maps key -> list index; one leader lane per distinct key of a batch does
 // the find-or-insert, new indices are handed out in lane order, duplicates are accumulated rank by rank as above.
+// Rows with at most 32 products and at most 32 stored entries of S: everything fits one 32-wide batch, so the row is
+// finished in registers - no shared-memory table.  Same arithmetic and the same first-occurrence order as
+// k_spgemm_fill_fo (duplicates of a key are added in ascending batch position, starting from the first one).  This is
+// the common row of the per-step delta products K E_t of the incremental K B (fit.cu), which the table kernel handled
+// at ~1 us of instructions per row.
+constexpr int TINY_MAX = 32;
+__global__ void __launch_bounds__(256)
+k_spgemm_tiny_fo(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
+                 const double* __restrict__ s_val, RowLists X, const long long* __restrict__ z_ptr,
+                 int* __restrict__ z_len, int* __restrict__ z_key, double* __restrict__ z_val) {
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < row_end; i += warps) {
+    const long long zp = z_ptr[i];
+    const long long ub = z_ptr[i + 1] - zp;
+    if (ub == 0) {
+      if (lane == 0) z_len[i] = 0;
+      continue;
+    }
+    const int s0 = s_ptr[i], s1 = s_ptr[i + 1];
+    if (ub > TINY_MAX || s1 - s0 > TINY_MAX) continue;  // k_spgemm_fill_fo takes this row
+    int q = -1, xl = 0;
+    double m = 0.0;
+    long long xp = 0;
+    if (s0 + lane < s1) {
+      q = s_col[s0 + lane];
+      m = s_val[s0 + lane];
+      xl = X.len[q];
+      xp = X.ptr[q];
+    }
+    int incl = xl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int tot = (int)ub;
+    const bool valid = lane < tot;
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int pv = __shfl_sync(FULL, incl, lo + step - 1);
+      if (pv <= lane) lo += step;
+    }
+    lo = min(lo, 31);
+    const int o_incl = __shfl_sync(FULL, incl, lo);
+    const int o_len = __shfl_sync(FULL, xl, lo);
+    const long long o_ptr = __shfl_sync(FULL, xp, lo);
+    const double o_m = __shfl_sync(FULL, m, lo);
+    int key = -1 - lane;
+    double c = 0.0;
+    if (valid) {
+      const long long e = o_ptr + (lane - (o_incl - o_len));
+      key = X.key[e];
+      c = __dmul_rn(o_m, X.val[e]);
+    }
+    const unsigned kgrp = __match_any_sync(FULL, key);
+    const bool leader = valid && (__ffs(kgrp) - 1) == lane;
+    const int maxcnt = __reduce_max_sync(FULL, valid ? __popc(kgrp) : 0);
+    unsigned rem = kgrp & ~(1u << lane);  // only meaningful on leaders: the other members, ascending
+    double acc = c;
+    for (int r = 1; r < maxcnt; ++r) {
+      const int src = rem ? (__ffs(rem) - 1) : lane;
+      const double v = __shfl_sync(FULL, c, src);
+      if (leader && rem) acc = __dadd_rn(acc, v);
+      rem &= rem - 1;
+    }
+    const unsigned lead = __ballot_sync(FULL, leader);
+    if (leader) {
+      const int pos = __popc(lead & lt_mask);
+      z_key[zp + pos] = key;
+      z_val[zp + pos] = acc;
+    }
+    if (lane == 0) z_len[i] = __popc(lead);
+  }
+}
+
 template <int CAP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spgemm_fill_fo(int row_begin, int row_end, const int* __restrict__ s_ptr, const int* __restrict__ s_col,
@@ -208,6 +287,7 @@ k_spgemm_fill_fo(int row_begin, int row_end, const int* __restrict__ s_ptr, cons
       if (lane == 0) z_len[i] = 0;
       continue;
     }
+    if (ub <= TINY_MAX && s_ptr[i + 1] - s_ptr[i] <= TINY_MAX) continue;  // done by k_spgemm_tiny_fo
     int cap = 64;
     while (cap < CAP && (long long)cap * 4 < 5 * ub) cap <<= 1;  // load factor <= 0.8 even if every key is distinct
     const int capm = cap - 1;
@@ -410,6 +490,8 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
                                         (int)smem_fo));
       attr_fo = true;
     }
+    SC_LAUNCH(ctx, k_spgemm_tiny_fo, std::min((rows + 7) / 8, 148 * 32), 256, 0, row_begin, row_end, S.indptr, S.indices,
+              S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p);
     SC_LAUNCH(ctx, (k_spgemm_fill_fo<CAP, WARPS>), grid, WARPS * 32, smem_fo, row_begin, row_end, S.indptr, S.indices,
               S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
   }

@@ -793,8 +793,7 @@ __global__ void k_row_max(int rows, RowLists L, double* __restrict__ mv, int* __
 }
 
 // Gradient of _updateB on the support of t2 (cpu.py:486): G[i,a] = 2 ((K B t1)[i,a] - t2[i,a]).
-// One chunk of one archetype's candidate list per CTA, one candidate per thread (rows of K B longer than UPB_LONG are
-// done by the whole warp afterwards).  Candidates are ordered by decreasing t2.  K, B, t1 >= 0 and monotone rounding
+// One chunk of one archetype's candidate list per CTA.  Candidates are ordered by decreasing t2.  K, B, t1 >= 0 and monotone rounding
 // give two exact lower bounds on the computed G[i,a]:
 //     G >= -2 t2[i,a]                                   (the product term is >= 0)
 //     G >= 2 (fl(KBmax_i * t1[lmax_i, a]) - t2[i,a])    (a sum of non-negative terms is >= any one of them)
@@ -802,7 +801,6 @@ __global__ void k_row_max(int rows, RowLists L, double* __restrict__ mv, int* __
 // bound exceeds it can neither be the argmin nor tie with it and is skipped without reading its K B row.  This is what
 // keeps long candidate lists affordable.  round 0 = first UPB_R0 candidates of every archetype,
 // round 1 = everything else.
-constexpr int UPB_LONG = 192;
 constexpr int UPB_R0 = 64;  // candidates evaluated unconditionally to seed the bound
 __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, const long long* __restrict__ chunk_ptr,
                                                       const int* __restrict__ chunk_arch,
@@ -862,11 +860,15 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   __syncthreads();
   const int nq = q_n;
   if (threadIdx.x == 0 && g.evaluated) atomicAdd(g.evaluated, (unsigned long long)nq);
-  // phase 2: exact gradient of the survivors, one per thread
+  // phase 2: exact gradient of the survivors.  A chunk keeps a few dozen of its 1024 candidates, so one survivor per
+  // thread would leave most of the CTA idle behind ~50 dependent gathers: 8 lanes share a survivor instead (lane s
+  // takes entries s, s+8, ... of the K B row, then a fixed xor tree), 32 survivors per pass.  The summation order is a
+  // function of the row alone, so the value of G[i,a] does not depend on chunking or sharding.
   double bv = FW_INF;
   int bi = 0x7fffffff;
-  for (int e0 = 0; e0 < nq; e0 += 256) {
-    const int e = e0 + threadIdx.x;
+  const int sub = threadIdx.x & 7;
+  for (int e0 = 0; e0 < nq; e0 += 32) {
+    const int e = e0 + (threadIdx.x >> 3);
     int cell = 0, L = 0;
     long long p = 0;
     double t2v = 0.0;
@@ -874,39 +876,27 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
     if (e < nq) {
       cell = q_cell[e];
       t2v = q_t2[e];
-      live = !(-2.0 * t2v > bv);  // the thread's own running minimum tightens the first bound further
+      live = !(-2.0 * t2v > bv);  // the group's own running minimum tightens the first bound further
       if (live) {
         p = g.KB.ptr[cell];
         L = g.KB.len[cell];
       }
     }
-    if (live && L <= UPB_LONG) {
-      double acc = 0.0;
+    double acc = 0.0;
+    if (live) {
       const int* __restrict__ kk = g.KB.key + p;
       const double* __restrict__ vv = g.KB.val + p;
-#pragma unroll 4
-      for (int x = 0; x < L; ++x) acc = fma(__ldg(vv + x), __ldg(row + __ldg(kk + x)), acc);
+#pragma unroll 2
+      for (int x = sub; x < L; x += 8) acc = fma(__ldg(vv + x), __ldg(row + __ldg(kk + x)), acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (live) {  // all 8 lanes of the group hold the same sum and keep the same running minimum
       const double G = 2.0 * (acc - t2v);
       if (G < bv || (G == bv && cell < bi)) {
         bv = G;
         bi = cell;
-      }
-    }
-    unsigned longmask = __ballot_sync(0xffffffffu, live && L > UPB_LONG);
-    while (longmask) {
-      const int src = __ffs(longmask) - 1;
-      longmask &= longmask - 1;
-      const long long pc = __shfl_sync(0xffffffffu, p, src);
-      const int Lc = __shfl_sync(0xffffffffu, L, src);
-      double acc = 0.0;
-      for (int x = lane; x < Lc; x += 32) acc = fma(g.KB.val[pc + x], row[g.KB.key[pc + x]], acc);
-      const double H = warp_sum(acc);
-      if (lane == src) {
-        const double G = 2.0 * (H - t2v);
-        if (G < bv || (G == bv && cell < bi)) {
-          bv = G;
-          bi = cell;
-        }
       }
     }
   }

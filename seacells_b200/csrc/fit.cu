@@ -124,17 +124,18 @@ __device__ __forceinline__ double list_lookup(const int* __restrict__ keys, cons
   return (lo < L && keys[lo] == key) ? vals[lo] : 0.0;
 }
 
-constexpr size_t FWA_PER_WARP =
-    (size_t)(FWA_NC + FWA_TCAP + FW_SMAX) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
+// per warp: candidate t2 values, running (t1 A)[candidates], running (t1 A)[archetypes 0..31], slot weights, candidate
+// ids, slot ids
+constexpr size_t FWA_PER_WARP = (size_t)(2 * FWA_NC + 32 + FW_SMAX) * sizeof(double) + (size_t)(FWA_NC + FW_SMAX) * sizeof(int);
 
-// Dense-column rule when no candidate is negative: scan archetypes 0,1,2,... and stop at the first exact zero of
-// G[i] = 2 (sum_s t1[i, act_s] a_s - t2[i]); if the column has no zero, return the first minimum.
+// Dense-column rule when no candidate is negative: scan archetypes i0, i0+1, ... and stop at the first exact zero of
+// G[i] = 2 (sum_s t1[i, act_s] a_s - t2[i]); if the column has no zero, return the first minimum (sv, si carry the
+// minimum of the part of the column that was already scanned).
 __device__ __forceinline__ int fwA_zero_scan(int k, const double* __restrict__ t1T, const int* act_id,
                                              const double* act_val, int nact, const int* ck, const double* ct2,
-                                             int nc, int lane) {
-  double sv = FW_INF;
-  int si = 0x7fffffff;
-  for (int i0 = 0; i0 < k; i0 += 32) {
+                                             int nc, int lane, int i_begin = 0, double sv = FW_INF,
+                                             int si = 0x7fffffff) {
+  for (int i0 = i_begin; i0 < k; i0 += 32) {
     const int i = i0 + lane;
     double G = FW_INF;
     if (i < k) {
@@ -153,17 +154,22 @@ __device__ __forceinline__ int fwA_zero_scan(int k, const double* __restrict__ t
   return si;
 }
 
-// Shared-memory path of _updateA: one warp per cell, candidates (support of t2[:, j]) and the t1 columns of the
-// active archetypes cached in shared memory.  Handles every cell with <= FWA_NC candidates when l2_penalty == 0,
-// including cells whose gradient has no negative entry (zero scan above; the chosen archetype then lies outside the
-// candidate set and simply becomes one more active slot).
+// Shared-memory path of _updateA: one warp per cell.  Handles every cell with <= FWA_NC candidates (support of
+// t2[:, j]) when l2_penalty == 0, including cells whose gradient has no negative entry (zero scan; the chosen archetype
+// then lies outside the candidate set and simply becomes one more active slot).
+// The step A <- A + gamma (e - A) moves t1 A by gamma (t1[:, chosen] - t1 A), so the products the gradient needs - on
+// the candidates, and on archetypes 0..31 where the zero scan almost always ends - are advanced in place instead of
+// being re-summed over the active slots at every step (that re-summation was ~25 t1 gathers per archetype and step
+// for the zero scan alone: 320 KB of L2 traffic per cell and call).  Exact zeros stay exact: a sum of non-negative
+// terms is zero iff every term is.
 __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* base = smem_raw + (size_t)warp * FWA_PER_WARP;
   double* ct2 = reinterpret_cast<double*>(base);
-  double* Tc = ct2 + FWA_NC;
-  double* sa = Tc + FWA_TCAP;
+  double* Hc = ct2 + FWA_NC;   // (t1 A)[ck[c]] for the current A
+  double* Hz = Hc + FWA_NC;    // (t1 A)[i], i < 32
+  double* sa = Hz + 32;
   int* ck = reinterpret_cast<int*>(sa + FW_SMAX);
   int* sid = ck + FWA_NC;
   const int k = g.k, S = g.S, T = g.T;
@@ -181,7 +187,6 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
       ct2[c] = g.KB.val[kp + c];
     }
     __syncwarp();
-    const int scap = nc > 0 ? min(FWA_TCAP / nc, FW_SMAX) : 0;
     // ---- t = 0: gradient against the previous A (cpu.py:447 with A = A_prev)
     const int m0 = g.Aprev.len[j];
     const int* pkey = g.Aprev.key + g.Aprev.ptr[j];
@@ -211,33 +216,39 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
       }
     }
     int nslots = 1;
+    const double a0 = fw_step(aprev, 1.0, fw_gamma(0));  // every other entry becomes a + (0 - a) = 0 and is dropped
     if (lane == 0) {
       sid[0] = chosen;
-      sa[0] = fw_step(aprev, 1.0, fw_gamma(0));  // every other entry becomes a + (0 - a) = 0 and is dropped
+      sa[0] = a0;
       if (g.trace) g.trace[j] = chosen;
     }
-    if (scap > 0)
-      for (int c = lane; c < nc; c += 32) Tc[c] = t1T[(size_t)chosen * k + ck[c]];
+    {
+      const double* __restrict__ trow = t1T + (size_t)chosen * k;
+      for (int c = lane; c < nc; c += 32) Hc[c] = __dmul_rn(trow[ck[c]], a0);
+      Hz[lane] = (lane < k) ? __dmul_rn(trow[lane], a0) : 0.0;
+    }
     __syncwarp();
     // ---- t >= 1
     for (int t = 1; t < T; ++t) {
       bv = FW_INF;
       bi = 0x7fffffff;
       for (int c = lane; c < nc; c += 32) {
-        double acc = 0.0;
-        const int id = ck[c];
-        for (int s = 0; s < nslots; ++s) {
-          const double tv = (s < scap) ? Tc[s * nc + c] : t1T[(size_t)sid[s] * k + id];
-          acc = fma(tv, sa[s], acc);
-        }
-        const double G = 2.0 * (acc - ct2[c]);
+        const double G = 2.0 * (Hc[c] - ct2[c]);
         if (G < bv) {
           bv = G;
           bi = c;
         }
       }
       warp_argmin(bv, bi);
-      chosen = (bv < 0.0) ? ck[bi] : fwA_zero_scan(k, t1T, sid, sa, nslots, ck, ct2, nc, lane);
+      if (bv < 0.0) {
+        chosen = ck[bi];
+      } else {
+        // dense-column rule: first exact zero, archetypes ascending; the first 32 come from the running product
+        const double Gz = (lane < k) ? 2.0 * (Hz[lane] - list_lookup(ck, ct2, nc, lane)) : FW_INF;
+        const unsigned z = __ballot_sync(0xffffffffu, Gz == 0.0);
+        if (z) chosen = __ffs(z) - 1;
+        else chosen = fwA_zero_scan(k, t1T, sid, sa, nslots, ck, ct2, nc, lane, 32, Gz, lane);
+      }
       const double gamma = fw_gamma(t);
       int pos = -1;
       for (int s0 = 0; s0 < nslots; s0 += 32) {
@@ -255,9 +266,12 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
           sid[nslots] = chosen;
           sa[nslots] = fw_step(0.0, 1.0, gamma);
         }
-        if (nslots < scap)
-          for (int c = lane; c < nc; c += 32) Tc[nslots * nc + c] = t1T[(size_t)chosen * k + ck[c]];
         nslots++;
+      }
+      {
+        const double* __restrict__ trow = t1T + (size_t)chosen * k;
+        for (int c = lane; c < nc; c += 32) Hc[c] = fw_step(Hc[c], trow[ck[c]], gamma);
+        if (lane < k) Hz[lane] = fw_step(Hz[lane], trow[lane], gamma);
       }
       if (lane == 0 && g.trace) g.trace[(size_t)t * g.n + j] = chosen;
       __syncwarp();

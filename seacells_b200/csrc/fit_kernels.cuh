@@ -32,7 +32,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 constexpr int FWA_NC = 128;     // max candidates per cell on the shared-memory path
-constexpr int FWA_TCAP = 1280;  // doubles of cached t1 columns per warp (768 and the higher occupancy it buys were measured slower)
-constexpr int FWA_WARPS = 4;
+constexpr int FWA_WARPS = 8;
 constexpr int FW_SMAX = 64;     // max slots per column supported by the kernels (>= max_FW_iter)
 constexpr double FW_INF = 1.0e300;

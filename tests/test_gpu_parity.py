@@ -243,6 +243,42 @@ def test_argmin_traces_vs_oracle():
         np.testing.assert_allclose(eng.rss(), O.compute_RSS(M, A, B), rtol=RSS_RTOL)
 
 
+def test_update_A_dense_column_rule_beyond_first_batch():
+    """_updateA's implicit-zero rule when the first exact zero of the gradient column lies beyond archetype 31: the
+    first 40 archetypes are 40 nearly coincident cells (mutually K-adjacent), so for the cells around them every one
+    of G[0..39] is non-zero.  The kernel keeps running products only for archetypes 0..31 and must continue the scan
+    with the full evaluation; every argmin has to equal the oracle's."""
+    rng = np.random.default_rng(0)
+    n, k = 900, 70
+    X = rng.normal(size=(n, 3)).astype(np.float32)
+    X[:45] = (rng.normal(size=(45, 3)) * 1e-3 + 5.0).astype(np.float32)
+    X[45:120] = (rng.normal(size=(75, 3)) * 0.05 + 5.0).astype(np.float32)
+    M, *_ = O.build_kernel(X.astype(np.float64), 15, "union")
+    K = sp.csr_matrix(M @ M.T)
+    arch = np.concatenate([np.arange(40), np.sort(rng.choice(np.arange(120, n), k - 40, replace=False))])
+    B = sp.csr_matrix((np.ones(k), (arch, np.arange(k))), shape=(n, k))
+    A = O.l1_normalise_columns(sp.csc_matrix((np.ones(n), (rng.integers(0, k, n), np.arange(n))), shape=(k, n)))
+    # the situation really occurs: non-negative gradient columns whose first zero is at index >= 32
+    t1 = np.asarray(((K @ B).T @ B).todense())
+    G = 2 * (t1 @ np.asarray(A.todense()) - np.asarray((K @ B).T.todense()))
+    first_zero = np.array([np.argmax(G[:, j] == 0) if (G[:, j] == 0).any() else -1 for j in range(n)])
+    assert ((G.min(0) >= 0) & (first_zero >= 32)).sum() >= 10
+    eng = _engine(n, k)
+    eng.set_kernel(M)
+    eng.set_archetypes(arch)
+    eng.set_A(A)
+    for outer in range(2):
+        trA, trB = [], []
+        A = O.update_A(K, B, A, 50, trace=trA)
+        gA = eng.update_A(0.0, trace=True)
+        assert np.array_equal(gA, np.array(trA)), f"_updateA argmin sequence, outer {outer}"
+        assert same_sparse(eng.A(), A)
+        B = O.update_B(K, A, B, 50, trace=trB)
+        gB = eng.update_B(trace=True)
+        assert np.array_equal(gB, np.array(trB)), f"_updateB argmin sequence, outer {outer}"
+        assert same_sparse(eng.B(), B)
+
+
 def test_isolated_cells_and_dead_archetypes():
     """Cells with no archetype within two hops (empty t2 column -> implicit-zero rule) and archetypes nobody uses."""
     n, k = 1200, 6

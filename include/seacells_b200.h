@@ -54,11 +54,11 @@ int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbo
  * Number of queries of the last call that needed the recomputation: */
 int sc_knn_fallback_rows(sc_ctx* ctx);
 /* Shortlist stage of the last sc_knn / sc_kernel_build call: out4 = { device milliseconds of the shortlist kernel (CUDA
- * events), kind (0 none, 1 fp32 FFMA tiles, 2 tcgen05 3xTF32), padded K of the tensor-core tiles, fallback rows }. */
+ * events), kind (0 none, 1 fp32 FFMA tiles, 2 tcgen05 split-fp16), padded K of the tensor-core tiles, fallback rows }. */
 int sc_knn_profile(sc_ctx* ctx, double* out4);
 
-/* The shortlist stage runs on the tensor cores (tcgen05, 3xTF32 split product) when d <= 63; SC_KNN_FFMA=1 forces the
- * fp32 FFMA tile kernel instead.  Test probe of that stage: s(i,j) = xi.xj - ||xj||^2/2 as the tensor cores computed it
+/* The shortlist stage runs on the tensor cores (tcgen05 kind::f16, split product x = hi + lo with two fp16 halves = the
+ * 22-bit operand precision of 3xTF32, fp32 accumulation) when d <= 127; SC_KNN_FFMA=1 forces the fp32 FFMA tile kernel.  Test probe of that stage: s(i,j) = xi.xj - ||xj||^2/2 as the tensor cores computed it
  * for the first 128 queries against references [0, cols)  (s_out [128 x cols]), plus the mean-centred fp32 embedding
  * (xc_out [n x d]) and its squared norms (norm2_out [n]) the products were formed from; host buffers.
  * sc_knn_tc_error_factor(d) is the certificate's bound on |(||xi||^2 - 2 s) - ||xi-xj||^2| / (||xi|| + ||xj||)^2. */

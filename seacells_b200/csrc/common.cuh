@@ -30,7 +30,7 @@ struct sc_ctx {
   unsigned long long launches = 0;
   int last_knn_fallback = 0;  // queries of the last kNN call that failed the filter certificate (recomputed exactly)
   float last_knn_filter_ms = 0.f;  // device time of the last shortlist kernel (CUDA events on the library stream)
-  int last_knn_filter_kind = 0;    // 0 none (all-fp64 kernel), 1 fp32 FFMA tiles, 2 tcgen05 3xTF32
+  int last_knn_filter_kind = 0;    // 0 none (all-fp64 kernel), 1 fp32 FFMA tiles, 2 tcgen05 split-fp16
   int last_knn_kp = 0;             // padded K of the tensor-core filter
 };
 

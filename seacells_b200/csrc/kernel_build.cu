@@ -392,8 +392,8 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
             maxnorm.p);
   double gamma;
   if (sc_knn_tc_supported(n, d) && getenv("SC_KNN_FFMA") == nullptr) {
-    // tensor-core filter (knn_tc.cu): 3xTF32 split product, fp32 accumulation in tensor memory
-    SC_TRY(sc_knn_filter_tc(ctx, Xc.p, norm2.p, n, d, row_begin, row_end, cand.p, thr.p, nullptr, 0));
+    // tensor-core filter (knn_tc.cu): 2xFP16 split product (22-bit operands), fp32 accumulation in tensor memory
+    SC_TRY(sc_knn_filter_tc(ctx, Xc.p, norm2.p, maxnorm.p, n, d, row_begin, row_end, cand.p, thr.p, nullptr, 0));
     gamma = sc_knn_tc_gamma(d);
   } else {
     const size_t smem = (size_t)KNN_DC * (KNN_QT + KNN_RT) * sizeof(float) +
@@ -450,7 +450,7 @@ int sc_knn_tc_probe_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, 
   SC_LAUNCH(ctx, k_col_mean, d, 256, 0, X, x_is_f64, n, d, mean.p);
   SC_LAUNCH(ctx, k_center, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, X, x_is_f64, n, d, mean.p, xc_out,
             norm2_out, maxnorm.p);
-  SC_TRY(sc_knn_filter_tc(ctx, xc_out, norm2_out, n, d, 0, rows, cand.p, thr.p, s_out, cols));
+  SC_TRY(sc_knn_filter_tc(ctx, xc_out, norm2_out, maxnorm.p, n, d, 0, rows, cand.p, thr.p, s_out, cols));
   return SC_OK;
 }
 

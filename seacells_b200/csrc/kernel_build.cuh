@@ -9,8 +9,8 @@ int sc_knn_exact_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int
 // squared distance; Xc / norm2 are the mean-centred fp32 embedding and its squared row norms
 bool sc_knn_tc_supported(int n, int d);
 double sc_knn_tc_gamma(int d);  // error bound factor of the 3xTF32 pipeline, see knn_tc.cu
-int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, int d, int row_begin, int row_end,
-                     int* cand_idx, float* cand_thr, float* dbg_s, int dbg_cols);
+int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, const float* maxnorm2, int n, int d, int row_begin,
+                     int row_end, int* cand_idx, float* cand_thr, float* dbg_s, int dbg_cols);
 int sc_knn_tc_probe_dev(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int cols, float* s_out, float* xc_out,
                         float* norm2_out);
 

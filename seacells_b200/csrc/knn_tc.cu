@@ -3,18 +3,24 @@
 // Replaces the distance contraction of scanpy.pp.neighbors (build_graph.py:125) for the filter stage of the exact kNN
 // (kernel_build.cu): for every query i and reference j it evaluates
 //        s(i,j) = xi.xj - ||xj||^2 / 2          (so that  ||xi-xj||^2 = ||xi||^2 - 2 s(i,j))
-// on the mean-centred fp32 embedding as a 3xTF32 split product
-//        A_hi B_hi + A_hi B_lo + A_lo B_hi,   x = hi + lo,  hi = tf32(x),  lo = tf32(x - hi)
+// on the mean-centred fp32 embedding as a split-precision product on the tensor cores
+//        A_hi B_hi + A_hi B_lo + A_lo B_hi,   x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)
 // with fp32 accumulation in tensor memory, and keeps the 32 references with the largest s per query together with the
-// 32nd value (the threshold of the certificate checked by k_knn_rerank).  The -||xj||^2/2 term rides along as one
-// extra K column (A holds 1 there), so the epilogue is a pure "is anything in this row chunk above my threshold" scan.
+// 32nd value (the threshold of the certificate checked by k_knn_rerank).  Two fp16 halves carry 22 significand bits -
+// the same operand precision as the classical 3xTF32 split (two 11-bit tf32 halves) - but kind::f16 MMAs run at twice
+// the tf32 rate for the same power, and the kernel is power-bound (the 3xTF32 version of this kernel held the 1 kW cap
+// at 558 ms for 1M x 50; see profiles/r1_knn_filter_tc.summary.txt).  The embedding is pre-scaled by a power of two so
+// that every |x| < 256 (exact; fp16 then never overflows and its subnormal floor 2^-25 is < 2^-32 of the largest norm,
+// which the error bound absorbs).  The -||xj||^2/2 term rides along as one extra K column (A holds 128 there, B holds
+// -||xj||^2 scale^2 / 256), so the epilogue is a pure "is anything in this row chunk above my threshold" scan.
 //
 // Layout
-//   references pre-tiled in global memory (k_knn_pack): one block of KP*1024 bytes per 128 cells = hi part + lo part,
+//   references pre-tiled in global memory (k_knn_pack): one block of KP*512 bytes per 128 cells = hi part + lo part,
 //              each already in the shared-memory image tcgen05.mma wants (K-major, no swizzle: 8x16-byte core
-//              matrices, row groups 128 B apart (SBO), K chunks 2048 B apart (LBO)); KP = round_up(d+1, 8).
+//              matrices = 8 rows x 8 halves, row groups 128 B apart (SBO), K chunks 2048 B apart (LBO));
+//              KP = round_up(d+1, 16).
 //   CTA        persistent, one per SM, 256 threads: warp 0 = bulk-copy producer (cp.async.bulk -> UBLKCP),
-//              warp 1 = MMA issuer (one thread; tcgen05.mma kind::tf32, M=128 N=128 K=8), warps 4-7 = epilogue
+//              warp 1 = MMA issuer (one thread; tcgen05.mma kind::f16, M=128 N=128 K=16), warps 4-7 = epilogue
 //              (tcgen05.ld 32x32b: one query row per thread).  The query tile (128 rows, hi and lo) lives in TENSOR
 //              MEMORY (written once per query tile by the epilogue threads with tcgen05.st, A operand of the MMAs):
 //              with both operands in shared memory the MMAs were bound by shared-memory bandwidth (8 KB of operand
@@ -28,6 +34,7 @@
 // Every mbarrier wait is bounded (2 s): a broken pipeline sets an error flag and drains instead of hanging the GPU.
 #include "kernel_build.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -107,13 +114,13 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // A operand from tensor memory (lane = row, column = k), B from shared memory
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                                uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -143,15 +150,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
 }
-// instruction descriptor: D fp32, A/B tf32, both K-major, N=128, M=128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+// instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, N=128, M=128
+constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                               ((uint32_t)(TC_M >> 4) << 24);
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// x -> (hi, lo) fp16 halves, bit patterns; x must already be scaled into fp16's range
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
 }
+// power-of-two scale that brings every centred |x| (<= the largest row norm) below 256; exact, same on every thread
+__device__ __forceinline__ float knn_scale(const float* __restrict__ maxnorm2) {
+  const float mn = sqrtf(maxnorm2[0]);
+  if (!(mn > 0.f) || !isfinite(mn)) return 1.f;
+  int e;
+  frexpf(mn, &e);  // mn = f * 2^e, 0.5 <= f < 1
+  return ldexpf(1.f, 8 - e);
+}
+constexpr float TC_ONE_COL = 128.f;  // value of the query tile's extra column; the references carry -||x||^2 scale^2 / 256
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
@@ -166,35 +184,38 @@ __device__ __forceinline__ uint32_t unordered_bits(uint32_t u) { return (u & 0x8
 }  // namespace
 
 // ---- operand packing --------------------------------------------------------------------------------------------
-// Reference tiles: one 16-byte unit (4 consecutive K columns of one cell) per thread, for the hi and the lo part.
-// Column d holds -||x||^2/2; rows past n get -1e30 there (never shortlisted) and zeros elsewhere.
-__global__ void k_knn_pack(const float* __restrict__ Xc, const float* __restrict__ norm2, int n, int d, int KP,
-                           float4* __restrict__ out) {
-  const int KC = KP >> 2;
+// Reference tiles: one 16-byte unit (8 consecutive K columns of one cell, fp16) per thread, for the hi and the lo part.
+// Column d holds -||x||^2 scale^2 / 256 (times the query tile's 128 = -||x||^2 scale^2 / 2); rows past n get -60000
+// there (never shortlisted) and zeros elsewhere.
+__global__ void k_knn_pack(const float* __restrict__ Xc, const float* __restrict__ norm2,
+                           const float* __restrict__ maxnorm2, int n, int d, int KP, uint4* __restrict__ out) {
+  const int KC = KP >> 3;
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_tiles = (n + TC_N - 1) / TC_N;
   if (u >= n_tiles * KC * 128) return;
+  const float scale = knn_scale(maxnorm2);
   const long long tile = u / (KC * 128);
   const int w = (int)(u - tile * (KC * 128));
   const int kc = w >> 7, r = w & 127;
   const long long cell = tile * 128 + r;
-  float hi[4], lo[4];
+  unsigned short hi[8], lo[8];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int c = kc * 4 + e;
+  for (int e = 0; e < 8; ++e) {
+    const int c = kc * 8 + e;
     float v = 0.f;
     if (cell < n) {
-      if (c < d) v = Xc[cell * d + c];
-      else if (c == d) v = -0.5f * norm2[cell];
+      if (c < d) v = Xc[cell * d + c] * scale;
+      else if (c == d) v = -norm2[cell] * scale * scale * (1.f / 256.f);
     } else if (c == d) {
-      v = -1e30f;
+      v = -60000.f;
     }
-    hi[e] = tf32_rna(v);
-    lo[e] = tf32_rna(v - hi[e]);
+    split_f16(v, hi[e], lo[e]);
   }
-  float4* tb = out + tile * (size_t)(2 * KC * 128);
-  tb[w] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  tb[KC * 128 + w] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  uint4* tb = out + tile * (size_t)(2 * KC * 128);
+  tb[w] = make_uint4(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16), hi[4] | ((uint32_t)hi[5] << 16),
+                     hi[6] | ((uint32_t)hi[7] << 16));
+  tb[KC * 128 + w] = make_uint4(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16),
+                                lo[4] | ((uint32_t)lo[5] << 16), lo[6] | ((uint32_t)lo[7] << 16));
 }
 
 // ---- the filter -------------------------------------------------------------------------------------------------
@@ -205,6 +226,7 @@ struct TcArgs {
   int d;
   const unsigned char* TB;   // packed reference tiles of all n cells
   const float* norm2;
+  const float* maxnorm2;     // largest squared row norm (fixes the power-of-two pre-scale)
   int n, KP, row_begin, row_end, n_q_tiles, n_r_tiles;
   int* cand_idx;             // [rows x 32]
   float* cand_thr;           // [rows]
@@ -281,7 +303,7 @@ __device__ __forceinline__ float compact_row(unsigned long long* __restrict__ ro
 __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t part_bytes = (uint32_t)a.KP * 512u;  // hi (or lo) part of one 128-row tile
+  const uint32_t part_bytes = (uint32_t)a.KP * 256u;  // hi (or lo) part of one 128-row tile (fp16)
   const uint32_t tile_bytes = 2u * part_bytes;
   unsigned char* sB = smem;  // TC_STAGES reference-tile stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * tile_bytes);
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
       bool ok = mbar_wait(BAR(B_A), qcount & 1u, abort_flag);  // query tile is in tensor memory
       ok = __all_sync(FULLMASK, ok);
       const uint32_t tA_hi = tmem_base + TC_COL_AHI, tA_lo = tmem_base + TC_COL_ALO;
-      const int ksteps = a.KP >> 3;
+      const int ksteps = a.KP >> 4;
       bool pre_ok = false;  // barriers of this tile were already seen complete while the previous tile was issued
       for (int rt = 0; ok && rt < a.n_r_tiles; ++rt, advance()) {
         if (!pre_ok) {
@@ -368,10 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         const uint32_t sb = smem_u32(sB) + s * tile_bytes;
         const uint64_t dB_hi = make_desc(sb), dB_lo = make_desc(sb + part_bytes);
         const uint32_t dtm = tmem_base + s * (uint32_t)TC_N;
-        // per K step (8 tf32): A advances 8 TMEM columns, B by 2 chunks = 2 * LBO = 4096 B = 256 descriptor units
+        // per K step (16 halves): A advances 8 TMEM columns, B by 2 chunks = 2 * LBO = 4096 B = 256 descriptor units
         if (leader) {
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_lo + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, k > 0);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_lo + (uint64_t)(k * 256), TC_IDESC, 1u);
+          for (int k = 0; k < ksteps; ++k) tc_mma_f16_ts(dtm, tA_lo + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, k > 0);
+          for (int k = 0; k < ksteps; ++k) tc_mma_f16_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_lo + (uint64_t)(k * 256), TC_IDESC, 1u);
         }
         __syncwarp();
         // the issue above blocks on the tensor pipe's queue; look at the next tile's barriers now, while the pipe
@@ -383,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
           pre_ok = __all_sync(FULLMASK, pre_ok);
         }
         if (leader) {
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, 1u);
+          for (int k = 0; k < ksteps; ++k) tc_mma_f16_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, 1u);
           tc_commit(BAR(B_EMPTY + s));  // shared-memory stage free once these MMAs have read it
           tc_commit(BAR(B_TFULL + s));  // accumulator ready for the epilogue
           TC_TRACE(3);
@@ -399,26 +421,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
       float thr = -INFINITY;
       int cnt = 0;
       bool ok = true;
+      const float inv_s2 = 1.f / (knn_scale(a.maxnorm2) * knn_scale(a.maxnorm2));  // power of two: exact
       {
-        // this thread's query row -> tensor memory: x = hi + lo (tf32 each), extra column d holds 1 (it multiplies
-        // the references' -||xj||^2/2 column), padding columns and rows past row_end are zero
+        // this thread's query row -> tensor memory: x = hi + lo (fp16 each, two elements per 32-bit column, the lower
+        // index in the low half), extra column d holds 128 (it multiplies the references' -||xj||^2 scale^2/256
+        // column), padding columns and rows past row_end are zero
         const long long grow = (long long)a.row_begin + (long long)qt * TC_M + row_in_tile;
         const bool live = grow < a.row_end;
         const float* __restrict__ xr = a.Xc + (size_t)(live ? grow : 0) * a.d;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int k8 = 0; k8 < (a.KP >> 3); ++k8) {
+        const float scale = knn_scale(a.maxnorm2);
+        for (int k16 = 0; k16 < (a.KP >> 4); ++k16) {
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int c = k8 * 8 + e;
-            float x = 0.f;
-            if (live) x = (c < a.d) ? xr[c] : (c == a.d ? 1.f : 0.f);
-            const float h = tf32_rna(x);
-            hi[e] = __float_as_uint(h);
-            lo[e] = __float_as_uint(tf32_rna(x - h));
+            unsigned short h2[2], l2[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int c = k16 * 16 + e * 2 + t;
+              float x = 0.f;
+              if (live) x = (c < a.d) ? xr[c] * scale : (c == a.d ? TC_ONE_COL : 0.f);
+              split_f16(x, h2[t], l2[t]);
+            }
+            hi[e] = h2[0] | ((uint32_t)h2[1] << 16);
+            lo[e] = l2[0] | ((uint32_t)l2[1] << 16);
           }
-          tc_st8(trow + TC_COL_AHI + (uint32_t)(k8 * 8), hi);
-          tc_st8(trow + TC_COL_ALO + (uint32_t)(k8 * 8), lo);
+          tc_st8(trow + TC_COL_AHI + (uint32_t)(k16 * 8), hi);
+          tc_st8(trow + TC_COL_ALO + (uint32_t)(k16 * 8), lo);
         }
         tc_wait_st();
         tc_fence_before();
@@ -431,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         if (a.dbg_s != nullptr && qt == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < a.dbg_cols) a.dbg_s[(size_t)row_in_tile * a.dbg_cols + col0 + j] = __uint_as_float(v[j]);
+            if (col0 + j < a.dbg_cols) a.dbg_s[(size_t)row_in_tile * a.dbg_cols + col0 + j] = __uint_as_float(v[j]) * inv_s2;
         }
         float g[4];
 #pragma unroll
@@ -528,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
           int idx = 0x7fffffff;
           if (lane < c) idx = (int)reinterpret_cast<const uint2*>(warpbuf)[(size_t)L * TC_CAP + lane].x;
           a.cand_idx[orow * TC_KEEP + lane] = idx;
-          if (lane == 0) a.cand_thr[orow] = (c >= TC_KEEP) ? fmaf(-2.f, t, a.norm2[grow]) : INFINITY;
+          if (lane == 0) a.cand_thr[orow] = (c >= TC_KEEP) ? fmaf(-2.f, t * inv_s2, a.norm2[grow]) : INFINITY;
         }
       }
     }
@@ -544,33 +573,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
+static inline int knn_tc_kp(int d) { return ((d + 1 + 15) / 16) * 16; }
+
 bool sc_knn_tc_supported(int n, int d) {
-  const int KP = ((d + 1 + 7) / 8) * 8;
-  return KP <= 64 && n >= 2048;  // 3 tiles of KP KB + barriers must fit the 227 KB of shared memory
+  return knn_tc_kp(d) <= 128 && n >= 2048;  // 3 stages of KP/2 KB + barriers fit the 227 KB of shared memory, A fits TMEM
 }
 
 // Error bound of the filter, as a multiple of (||xi|| + ||xj||)^2, for |(||xi||^2 - 2 s_computed) - ||xi - xj||^2|:
-//   * operand split: x = hi + lo + r with |r| <= 2^-22 |x| (two tf32 roundings), and the dropped lo*lo products
-//     <= 2^-22 |xi||xj| per term                                             -> 3 * 2^-22 per unit of sum |xi_c||xj_c|
-//   * tf32 x tf32 products are exact in fp32; each of the 3*KP accumulations loses at most one fp32 ulp (2^-23,
+//   * operand split: x = hi + lo + r with |r| <= 2^-22 |x| (two fp16 roundings, 11 significant bits each; the
+//     pre-scale keeps every |x| < 256, so the subnormal floor 2^-25 is below 2^-32 of the largest norm), and the dropped
+//     lo*lo products <= 2^-22 |xi||xj| per term                               -> 3 * 2^-22 per unit of sum |xi_c||xj_c|
+//   * fp16 x fp16 products are exact in fp32; each of the 3*KP accumulations loses at most one fp32 ulp (2^-23,
 //     truncation allowed) of a partial sum bounded by ||xi|| ||xj|| + ||xj||^2 / 2
 //   => |error(s)| <= (3*2^-22 + 3*KP*2^-23) (||xi|| ||xj|| + ||xj||^2/2) <= half that times (||xi|| + ||xj||)^2,
 //      and the distance carries 2 * error(s):  (12 + 6 KP) u  with u = 2^-24,
-//   * plus the fp32 centring / norm / final-combination terms of the FFMA filter's bound, (d + 8) u.
+//   * plus the fp32 centring / norm / final-combination terms of the FFMA filter's bound, (d + 8) u, and 4 u for the
+//     subnormal floor.
 // The whole bound is doubled.  tests/test_gpu_parity.py measures the realised error against it (sc_knn_tc_probe).
 double sc_knn_tc_gamma(int d) {
-  const int KP = ((d + 1 + 7) / 8) * 8;
-  return 2.0 * (double)(6 * KP + 12 + d + 8) * 5.9604644775390625e-08;
+  const int KP = knn_tc_kp(d);
+  return 2.0 * (double)(6 * KP + 12 + d + 8 + 4) * 5.9604644775390625e-08;
 }
 
-int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, int d, int row_begin, int row_end,
+int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, const float* maxnorm2, int n, int d, int row_begin,
+                     int row_end,
                      int* cand_idx, float* cand_thr, float* dbg_s, int dbg_cols) {
-  const int KP = ((d + 1 + 7) / 8) * 8;
+  const int KP = knn_tc_kp(d);
   if (!sc_knn_tc_supported(n, d)) SC_FAIL(ctx, SC_ERR_ARG, "knn tensor-core filter: unsupported shape");
   const int rows = row_end - row_begin;
   if (rows <= 0) return SC_OK;
   const int n_q_tiles = (rows + TC_M - 1) / TC_M, n_r_tiles = (n + TC_N - 1) / TC_N;
-  const size_t tile_bytes = (size_t)KP * 1024;
+  const size_t tile_bytes = (size_t)KP * 512;
   int dev = 0, sms = 0;
   SC_CUDA(ctx, cudaGetDevice(&dev));
   SC_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -583,14 +616,16 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, int n, in
   SC_TRY(err.ensure(ctx, 4));
   SC_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int) * 4, ctx->stream));
   {
-    const long long units = (long long)n_r_tiles * (KP / 4) * 128;
-    SC_LAUNCH(ctx, k_knn_pack, (unsigned)((units + 255) / 256), 256, 0, Xc, norm2, n, d, KP, reinterpret_cast<float4*>(TB.p));
+    const long long units = (long long)n_r_tiles * (KP / 8) * 128;
+    SC_LAUNCH(ctx, k_knn_pack, (unsigned)((units + 255) / 256), 256, 0, Xc, norm2, maxnorm2, n, d, KP,
+              reinterpret_cast<uint4*>(TB.p));
   }
   TcArgs a;
   a.Xc = Xc;
   a.d = d;
   a.TB = TB.p;
   a.norm2 = norm2;
+  a.maxnorm2 = maxnorm2;
   a.n = n;
   a.KP = KP;
   a.row_begin = row_begin;

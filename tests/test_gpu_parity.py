@@ -106,8 +106,8 @@ def test_knn_filter_path_is_exact():
 
 
 def test_knn_tensor_core_filter():
-    """tcgen05 shortlist stage (d <= 63): realised error of the 3xTF32 split product against the bound the certificate
-    uses, on benign and on badly scaled data; the FFMA filter (d > 63) and the tensor-core filter both stay exact."""
+    """tcgen05 shortlist stage (d <= 127): realised error of the 2xFP16 split product against the bound the certificate
+    uses, on benign and on badly scaled data; the FFMA filter (d > 127) and the tensor-core filter both stay exact."""
     from seacells_b200 import _lib, knn
     from seacells_b200.synth import synth_embedding
     ctx = _lib.default_context()
@@ -132,11 +132,19 @@ def test_knn_tensor_core_filter():
         idx, d2 = knn(X, 15)
         io, do = O.knn_exact(X, 15)
         assert np.array_equal(idx, io) and np.array_equal(d2, do)
-    # d > 63: FFMA filter
-    X = rng.normal(size=(3000, 70)).astype(np.float32)
-    idx, d2 = knn(X, 15)
-    io, do = O.knn_exact(X, 15)
-    assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    # 63 < d <= 127: still the tensor-core filter (KP up to 128); d > 127: fp32 FFMA tile filter
+    for d in (70, 127, 130):
+        X = rng.normal(size=(2500, d)).astype(np.float32)
+        idx, d2 = knn(X, 15)
+        io, do = O.knn_exact(X, 15)
+        assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    # values far outside fp16's range (the pre-scale is a power of two taken from the largest row norm)
+    for s in (1e-6, 1e6):
+        X = (synth_embedding(3000, 20, 2) * s).astype(np.float32)
+        idx, d2 = knn(X, 15)
+        io, do = O.knn_exact(X, 15)
+        assert np.array_equal(idx, io) and np.array_equal(d2, do)
+        assert ctx.lib.sc_knn_fallback_rows(ctx.h) == 0
     # query slab (a rank's shard) through the tensor-core filter, not a multiple of the tile
     X = synth_embedding(5000, 50, 4)
     io, do = O.knn_exact(X, 15)

@@ -1311,6 +1311,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
   profile = std::getenv("SC_PROFILE") != nullptr;
   fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
+  if (const char* e = std::getenv("SC_HUB_MAX")) hub_cap = std::max(0, std::min(HUB_MAX, atoi(e)));
   n = n_;
   row_begin = 0;
   row_end = n_;
@@ -1721,7 +1722,7 @@ int sc_fit::update_B_begin() {
     for (int a = 0; a < k; ++a)
       if (hc[a + 1] - hc[a] > thr) big.push_back({-(hc[a + 1] - hc[a]), a});
     std::sort(big.begin(), big.end());
-    if ((int)big.size() > HUB_MAX) big.resize(HUB_MAX);
+    if ((int)big.size() > hub_cap) big.resize(hub_cap);
     std::vector<int> ids, slot(k, -1);
     for (auto& b : big) ids.push_back(b.second);
     std::sort(ids.begin(), ids.end());

@@ -37,6 +37,7 @@ struct sc_fit {
   // incremental K B inside one _updateB call: chosen cells of the last step, E by cell, M E, K E, second K B buffer
   DBuf<int> amin_cur;
   RowListsBuf erow, EY, DKB, KB2;
+  int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   DBuf<long long> b_off;
   DBuf<unsigned long long> bk_in, bk_out;

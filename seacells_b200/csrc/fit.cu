@@ -777,9 +777,9 @@ __global__ void k_perm_unpack(int count, const unsigned long long* __restrict__ 
 }
 
 // largest entry of every K B row: (value, archetype); feeds the second pruning bound of k_updateB_eval
-__global__ void k_row_max(int rows, RowLists L, double* __restrict__ mv, int* __restrict__ ml) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+__global__ void k_row_max(int r0, int r1, RowLists L, double* __restrict__ mv, int* __restrict__ ml) {
+  const int warp = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= r1) return;
   const long long p = L.ptr[warp];
   const int len = L.len[warp];
   double bv = -1.0;
@@ -1103,12 +1103,37 @@ __global__ void k_merge_len(int n, const int* __restrict__ la, const int* __rest
 // keys that are new to the row are appended in D's order (both orders are fixed => bitwise reproducible).
 __global__ void __launch_bounds__(256)
 k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict__ new_ptr, int* __restrict__ new_len,
-           int* __restrict__ new_key, double* __restrict__ new_val, double c_old, double c_new) {
+           int* __restrict__ new_key, double* __restrict__ new_val, double c_old, double c_new,
+           double* __restrict__ max_v, int* __restrict__ max_l) {
   const int lane = threadIdx.x & 31;
   const int i = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (i >= r1) return;
   const int lo = Old.len[i], ld = D.len[i];
   const long long po = Old.ptr[i], pd = D.ptr[i], pn = new_ptr[i];
+  // the row's largest entry (value, then smaller key) rides along: it feeds the second pruning bound of k_updateB_eval
+  double bv = -1.0;
+  int bk = 0x7fffffff;
+  auto track = [&](double v, int key) {
+    if (v > bv || (v == bv && key < bk)) {
+      bv = v;
+      bk = key;
+    }
+  };
+  auto finish_max = [&]() {
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, dd);
+      const int ok2 = __shfl_xor_sync(0xffffffffu, bk, dd);
+      if (ov > bv || (ov == bv && ok2 < bk)) {
+        bv = ov;
+        bk = ok2;
+      }
+    }
+    if (lane == 0) {
+      max_v[i] = bv > 0.0 ? bv : 0.0;
+      max_l[i] = bv > 0.0 ? bk : 0;
+    }
+  };
   if (ld <= 32) {
     // common case: the delta row fits one batch - one pass over the old row
     const bool dvd = lane < ld;
@@ -1129,16 +1154,20 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
       if (ov) {
         new_key[pn + ob + lane] = ok;
         new_val[pn + ob + lane] = val;
+        track(val, ok);
       }
     }
     const bool app = dvd && !matched;
     const unsigned ball = __ballot_sync(0xffffffffu, app);
     if (app) {
       const int pos = lo + __popc(ball & ((1u << lane) - 1u));
+      const double nv = __dmul_rn(c_new, dv);
       new_key[pn + pos] = dk;
-      new_val[pn + pos] = __dmul_rn(c_new, dv);
+      new_val[pn + pos] = nv;
+      track(nv, dk);
     }
     if (lane == 0) new_len[i] = lo + __popc(ball);
+    finish_max();
     return;
   }
   // old entries, scaled, plus the matching delta entry if there is one
@@ -1160,6 +1189,7 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
     if (ov) {
       new_key[pn + ob + lane] = ok;
       new_val[pn + ob + lane] = val;
+      track(val, ok);
     }
   }
   // delta entries whose key is new to the row
@@ -1178,12 +1208,15 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
     const unsigned ball = __ballot_sync(0xffffffffu, app);
     if (app) {
       const int pos = lo + napp + __popc(ball & ((1u << lane) - 1u));
+      const double nv = __dmul_rn(c_new, dv);
       new_key[pn + pos] = dk;
-      new_val[pn + pos] = __dmul_rn(c_new, dv);
+      new_val[pn + pos] = nv;
+      track(nv, dk);
     }
     napp += __popc(ball);
   }
   if (lane == 0) new_len[i] = lo + napp;
+  finish_max();
 }
 
 // ------------------------------------------------------------------------------------------------ RSS, labels
@@ -1519,7 +1552,7 @@ int sc_fit::advance_KB(int t) {
     const int rows = row_end - row_begin;
     if (rows > 0)
       SC_LAUNCH(ctx, k_kb_merge, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, row_begin, row_end, KB.view(),
-                DKB.view(), KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p, 1.0 - gamma, gamma);
+                DKB.view(), KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p, 1.0 - gamma, gamma, cmax_v.p, cmax_l.p);
     swap_lists(KB, KB2);
   }
   pstop(P_SPGEMM_KB);
@@ -1535,7 +1568,8 @@ int sc_fit::build_perm() {
   SC_TRY(pk_in.ensure(ctx, (size_t)nloc + 1));
   SC_TRY(pk_out.ensure(ctx, (size_t)nloc + 1));
   if (nloc == 0) return SC_OK;
-  SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
+  SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)nloc * 32 + 255) / 256), 256, 0, row_begin, row_end, KB.view(), cmax_v.p,
+            cmax_l.p);
   SC_LAUNCH(ctx, k_perm_keys, (nloc + 255) / 256, 256, 0, row_begin, row_end, cmax_l.p, pk_in.p);
   int kb = 1;
   while ((1ll << kb) < k) kb++;
@@ -1806,7 +1840,10 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
   if (t == 0 && n_hub > 0) SC_TRY(build_perm());  // the order only affects locality; reused for the remaining steps
   if (nchunks > 0) {
-    SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), cmax_v.p, cmax_l.p);
+    // largest entry of every K B row (second pruning bound): produced by k_kb_merge when it ran, else computed here
+    if (t < 2 || fresh_kb)
+      SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)(row_end - row_begin) * 32 + 255) / 256), 256, 0, row_begin, row_end,
+                KB.view(), cmax_v.p, cmax_l.p);
     SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
               bound_v.p);
     SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,

@@ -152,6 +152,31 @@ def test_knn_tensor_core_filter():
     assert np.array_equal(pi, io[1234:2534]) and np.array_equal(pd, do[1234:2534])
 
 
+def test_knn_tensor_core_filter_degenerate_inputs():
+    """Low-dimensional embeddings, more exact duplicates than the shortlist holds (every tie at the threshold must fall
+    back to the exact kernel), a constant column, and n that is not a multiple of the 128-row tiles."""
+    from seacells_b200 import _lib, knn
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(23)
+    X = rng.normal(size=(3001, 2)).astype(np.float32)
+    X[100:150] = X[99]                      # 51 identical points: their 14 nearest neighbours are all at distance 0
+    idx, d2 = knn(X, 15)
+    io, do = O.knn_exact(X, 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    assert ctx.lib.sc_knn_fallback_rows(ctx.h) >= 51
+    X = rng.normal(size=(2049, 5)).astype(np.float32)
+    X[:, 3] = 7.25                          # constant column (centred to exactly 0)
+    idx, d2 = knn(X, 15)
+    io, do = O.knn_exact(X, 15)
+    assert np.array_equal(idx, io) and np.array_equal(d2, do)
+    for first in (1.0, 0.0):                # (almost) all points identical: nothing but ties; largest norm exactly 0
+        X = np.zeros((2100, 4), np.float32)
+        X[0] = first
+        idx, d2 = knn(X, 6)
+        io, do = O.knn_exact(X, 6)
+        assert np.array_equal(idx, io) and np.array_equal(d2, do)
+
+
 def test_spmm_csr_dense():
     from seacells_b200 import spmm_csr
     rng = np.random.default_rng(0)

@@ -19,9 +19,9 @@
 //              each already in the shared-memory image tcgen05.mma wants (K-major, no swizzle: 8x16-byte core
 //              matrices = 8 rows x 8 halves, row groups 128 B apart (SBO), K chunks 2048 B apart (LBO));
 //              KP = round_up(d+1, 16).
-//   CTA        persistent, one per SM, 256 threads: warp 0 = bulk-copy producer (cp.async.bulk -> UBLKCP),
-//              warp 1 = MMA issuer (one thread; tcgen05.mma kind::f16, M=128 N=128 K=16), warps 4-7 = epilogue
-//              (tcgen05.ld 32x32b: one query row per thread).  The query tile (128 rows, hi and lo) lives in TENSOR
+//   CTA        persistent, one per SM, 384 threads: warp 0 = bulk-copy producer (cp.async.bulk -> UBLKCP),
+//              warp 1 = MMA issuer (one thread; tcgen05.mma kind::f16, M=128 N=128 K=16), warps 4-11 = epilogue
+//              (tcgen05.ld 32x32b: a query row is shared by two threads, one per 64-column half of the tile).  The query tile (128 rows, hi and lo) lives in TENSOR
 //              MEMORY (written once per query tile by the epilogue threads with tcgen05.st, A operand of the MMAs):
 //              with both operands in shared memory the MMAs were bound by shared-memory bandwidth (8 KB of operand
 //              reads per 64-cycle MMA next to the bulk copies: 95 cycles per MMA measured).  Reference tiles stream
@@ -49,7 +49,7 @@ namespace {
 
 constexpr int TC_M = 128;          // queries per CTA tile
 constexpr int TC_N = 128;          // references per streamed tile
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;    // producer warp, MMA warp, 2 idle, 8 epilogue warps
 constexpr int TC_CAP = 128;        // append-buffer entries per row
 constexpr int TC_TRIG = 96;        // compact when a row holds more than this after a chunk
 constexpr int TC_KEEP = 32;        // shortlist size (== KF_NC in kernel_build.cu)
@@ -406,6 +406,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
   // bars[0..2] full, [3..5] empty, [6..8] tmem full, [9..11] tmem empty, [12] query tile written to TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  // the two epilogue threads of a row (column halves) publish their thresholds and final counts here
+  volatile float* sthr = reinterpret_cast<volatile float*>(smem + TC_STAGES * tile_bytes + 128);  // [2][TC_M]
+  volatile int* scnt = reinterpret_cast<volatile int*>(sthr + 2 * TC_M);                          // [2][TC_M]
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_FULL = 0, B_EMPTY = 3, B_TFULL = 6, B_TEMPTY = 9, B_A = 12;
@@ -415,12 +418,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
       mbar_init(BAR(B_FULL + b), 1);
       mbar_init(BAR(B_EMPTY + b), 1);
       mbar_init(BAR(B_TFULL + b), 1);
-      mbar_init(BAR(B_TEMPTY + b), 4);
+      mbar_init(BAR(B_TEMPTY + b), 8);
     }
     mbar_init(BAR(B_A), 4);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 2 * TC_M) sthr[tid] = -INFINITY;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TC_TMEM_COLS)
@@ -511,16 +515,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         __syncwarp();
       }
     } else if (warp >= 4) {
-      // ===== epilogue: one query row per thread =====
-      const int q = warp & 3;
+      // ===== epilogue: 8 warps; a query row is shared by two threads (lane quadrant q = warp % 4 as tcgen05.ld demands,
+      // column half h): each keeps the best 32 of its half of every tile, the halves are merged at the end.  The larger
+      // of the two thresholds bounds both (the union's 32nd best is at least either half's). =====
+      const int q = warp & 3, h = (warp - 4) >> 2;
       const int row_in_tile = q * 32 + lane;
-      unsigned long long* rowbuf = a.scratch + ((size_t)blockIdx.x * TC_M + row_in_tile) * TC_CAP;
-      unsigned long long* warpbuf = a.scratch + ((size_t)blockIdx.x * TC_M + q * 32) * TC_CAP;
+      unsigned long long* rowbuf = a.scratch + (((size_t)blockIdx.x * 2 + h) * TC_M + row_in_tile) * TC_CAP;
+      unsigned long long* warpbuf = a.scratch + (((size_t)blockIdx.x * 2 + h) * TC_M + q * 32) * TC_CAP;
+      unsigned long long* otherbuf = a.scratch + (((size_t)blockIdx.x * 2 + (1 - h)) * TC_M + q * 32) * TC_CAP;
       float thr = -INFINITY;
       int cnt = 0;
       bool ok = true;
       const float inv_s2 = 1.f / (knn_scale(a.maxnorm2) * knn_scale(a.maxnorm2));  // power of two: exact
-      {
+      if (h == 0) {
         // this thread's query row -> tensor memory: x = hi + lo (fp16 each, two elements per 32-bit column, the lower
         // index in the low half), extra column d holds 128 (it multiplies the references' -||xj||^2 scale^2/256
         // column), padding columns and rows past row_end are zero
@@ -597,8 +604,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
             const int c = __shfl_sync(FULLMASK, cnt, L);
             const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
             if (lane == L) {
-              thr = t;
+              thr = fmaxf(thr, t);
               cnt = TC_KEEP;
+              sthr[h * TC_M + row_in_tile] = thr;
             }
           }
         }
@@ -609,32 +617,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         if (!ok) break;
         if (warp == 4 && lane == 0) TC_TRACE(4);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)TC_N;
-        const int colt = tile_seq(rt, ctile, a.n_r_tiles) * TC_N;
+        thr = fmaxf(thr, sthr[(1 - h) * TC_M + row_in_tile]);  // the other half's threshold is valid for this half too
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)TC_N + (uint32_t)(h * 64);
+        const int colt = tile_seq(rt, ctile, a.n_r_tiles) * TC_N + h * 64;
         {
-          // software pipeline over the 4 chunks: the tensor-memory load of the next chunk is in flight while this
-          // one is scanned
+          // the tensor-memory load of the second chunk is in flight while the first one is scanned
           uint32_t va[32], vb[32];
           tc_ld32(tbase, va);
           tc_wait_ld();
           tc_ld32(tbase + 32, vb);
           scan_chunk(va, colt);
           tc_wait_ld();
-          tc_ld32(tbase + 64, va);
-          scan_chunk(vb, colt + 32);
-          tc_wait_ld();
-          tc_ld32(tbase + 96, vb);
-          scan_chunk(va, colt + 64);
-          tc_wait_ld();
-          // everything of this accumulator buffer is in registers: hand it back before the last scan
+          // everything this warp needs of the accumulator buffer is in registers: hand it back before the last scan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_TEMPTY + s));
-          scan_chunk(vb, colt + 96);
+          scan_chunk(vb, colt + 32);
         }
         if (warp == 4 && lane == 0) TC_TRACE(5);
       }
-      // final shortlist of the 32 rows of this warp
+      // final shortlist of this half of the warp's 32 rows
       __syncwarp();
       {
         unsigned need = __ballot_sync(FULLMASK, cnt > TC_KEEP);
@@ -644,26 +646,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
           const int c = __shfl_sync(FULLMASK, cnt, L);
           const float t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
           if (lane == L) {
-            thr = t;
+            thr = fmaxf(thr, t);
             cnt = TC_KEEP;
           }
         }
       }
-      __syncwarp();
-      for (int L = 0; L < 32; ++L) {
-        const int c = __shfl_sync(FULLMASK, cnt, L);
-        const float t = __shfl_sync(FULLMASK, thr, L);
-        const long long qpos = (long long)qt * TC_M + q * 32 + L;
-        if (ok && qpos < (long long)(a.row_end - a.row_begin)) {
-          const int grow = a.qorder[qpos];
-          const size_t orow = (size_t)(grow - a.row_begin);
-          int idx = 0x7fffffff;
-          if (lane < c) {
-            const int pos = (int)reinterpret_cast<const uint2*>(warpbuf)[(size_t)L * TC_CAP + lane].x;
-            idx = pos < a.n ? a.order[pos] : 0x7fffffff;
+      scnt[h * TC_M + row_in_tile] = cnt;
+      sthr[h * TC_M + row_in_tile] = -INFINITY;  // reset for the next query tile (the other half may still read it: harmless)
+      __threadfence_block();
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps: both halves of every row are final
+      if (h == 0) {
+        // merge the two halves: append the other half's entries to this buffer, keep the best 32 of the union
+        for (int L = 0; L < 32; ++L) {
+          const int c0 = __shfl_sync(FULLMASK, cnt, L);
+          const int c1 = scnt[TC_M + q * 32 + L];
+          if (lane < c1)
+            warpbuf[(size_t)L * TC_CAP + c0 + lane] = otherbuf[(size_t)L * TC_CAP + lane];
+          __syncwarp();
+          const int c = c0 + c1;
+          float t = -INFINITY;
+          if (c > TC_KEEP) t = compact_row(warpbuf + (size_t)L * TC_CAP, c, lane);
+          const int cf = min(c, TC_KEEP);
+          const long long qpos = (long long)qt * TC_M + q * 32 + L;
+          if (ok && qpos < (long long)(a.row_end - a.row_begin)) {
+            const int grow = a.qorder[qpos];
+            const size_t orow = (size_t)(grow - a.row_begin);
+            int idx = 0x7fffffff;
+            if (lane < cf) {
+              const int pos = (int)reinterpret_cast<const uint2*>(warpbuf)[(size_t)L * TC_CAP + lane].x;
+              idx = pos < a.n ? a.order[pos] : 0x7fffffff;
+            }
+            a.cand_idx[orow * TC_KEEP + lane] = idx;
+            if (lane == 0) a.cand_thr[orow] = (c > TC_KEEP) ? fmaf(-2.f, t * inv_s2, a.norm2[grow]) : INFINITY;
           }
-          a.cand_idx[orow * TC_KEEP + lane] = idx;
-          if (lane == 0) a.cand_thr[orow] = (c >= TC_KEEP) ? fmaf(-2.f, t * inv_s2, a.norm2[grow]) : INFINITY;
         }
       }
     }
@@ -719,7 +734,7 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, const flo
   DBuf<int> err, order, inv, qorder;
   DBuf<char> stmp;
   SC_TRY(TB.ensure(ctx, (size_t)n_r_tiles * tile_bytes));
-  SC_TRY(scratch.ensure(ctx, (size_t)grid * TC_M * TC_CAP));
+  SC_TRY(scratch.ensure(ctx, (size_t)grid * 2 * TC_M * TC_CAP));
   SC_TRY(err.ensure(ctx, 4));
   SC_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int) * 4, ctx->stream));
   {
@@ -775,7 +790,7 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, const flo
     a.trace = trace.p;
     a.trace_off = getenv("SC_KNN_TC_TRACE_OFF") ? atoi(getenv("SC_KNN_TC_TRACE_OFF")) : 0;
   }
-  const size_t smem = TC_STAGES * tile_bytes + 128;
+  const size_t smem = TC_STAGES * tile_bytes + 128 + 4 * TC_M * sizeof(float);
   SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   SC_CUDA(ctx, cudaEventCreate(&e0));

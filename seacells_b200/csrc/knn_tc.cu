@@ -25,7 +25,7 @@
 //              MEMORY (written once per query tile by the epilogue threads with tcgen05.st, A operand of the MMAs):
 //              with both operands in shared memory the MMAs were bound by shared-memory bandwidth (8 KB of operand
 //              reads per 64-cycle MMA next to the bulk copies: 95 cycles per MMA measured).  Reference tiles stream
-//              through a 3-stage ring; accumulators are triple buffered in TMEM (3 x 128 columns) so the MMAs of the
+//              through a ring of up to 6 stages (as many as fit: in-flight bytes hide the L2 latency); accumulators are triple buffered in TMEM (3 x 128 columns) so the MMAs of the
 //              next tiles run under the scan of this one.  TMEM map: [0,384) accumulators, [384,448) A hi, [448,512) A lo.
 //   selection  per row: threshold register + append buffer (128 entries, L2-resident scratch); a row whose buffer
 //              passes 96 entries is compacted to its best 32 by the whole warp (bitwise radix select over votes).
@@ -54,7 +54,8 @@ constexpr int TC_CAP = 128;        // append-buffer entries per row
 constexpr int TC_TRIG = 96;        // compact when a row holds more than this after a chunk
 constexpr int TC_KEEP = 32;        // shortlist size (== KF_NC in kernel_build.cu)
 constexpr int TC_TMEM_COLS = 512;  // 3 accumulator buffers x 128 fp32 columns + the query tile (hi, lo: 64 columns each)
-constexpr int TC_STAGES = 3;
+constexpr int TC_ACC = 3;          // accumulator buffers in tensor memory
+constexpr int TC_MAX_STAGES = 6;   // reference-tile stages in shared memory: as many as fit (<= 6), chosen on the host
 constexpr uint32_t TC_COL_AHI = 384, TC_COL_ALO = 448;
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -323,7 +324,7 @@ struct TcArgs {
   const int* order;          // [n] Morton position -> cell (reference tiles are packed in this order)
   const int* inv;            // [n] cell -> Morton position
   const int* qorder;         // [rows] query position -> cell (the queries of this call in Morton order)
-  int n, KP, row_begin, row_end, n_q_tiles, n_r_tiles;
+  int n, KP, row_begin, row_end, n_q_tiles, n_r_tiles, stages;
   int* cand_idx;             // [rows x 32]
   float* cand_thr;           // [rows]
   unsigned long long* scratch;  // [gridDim.x x 128 rows x TC_CAP]
@@ -401,22 +402,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t part_bytes = (uint32_t)a.KP * 256u;  // hi (or lo) part of one 128-row tile (fp16)
   const uint32_t tile_bytes = 2u * part_bytes;
-  unsigned char* sB = smem;  // TC_STAGES reference-tile stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * tile_bytes);
-  // bars[0..2] full, [3..5] empty, [6..8] tmem full, [9..11] tmem empty, [12] query tile written to TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  unsigned char* sB = smem;  // a.stages reference-tile stages
+  const uint32_t NS = (uint32_t)a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * tile_bytes);
+  // bars[0..5] full, [6..11] empty, [12..14] tmem full, [15..17] tmem empty, [18] query tile written to TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
   // the two epilogue threads of a row (column halves) publish their thresholds and final counts here
-  volatile float* sthr = reinterpret_cast<volatile float*>(smem + TC_STAGES * tile_bytes + 128);  // [2][TC_M]
+  volatile float* sthr = reinterpret_cast<volatile float*>(smem + NS * tile_bytes + 256);  // [2][TC_M]
   volatile int* scnt = reinterpret_cast<volatile int*>(sthr + 2 * TC_M);                          // [2][TC_M]
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_FULL = 0, B_EMPTY = 3, B_TFULL = 6, B_TEMPTY = 9, B_A = 12;
+  constexpr int B_FULL = 0, B_EMPTY = TC_MAX_STAGES, B_TFULL = 2 * TC_MAX_STAGES, B_TEMPTY = 2 * TC_MAX_STAGES + TC_ACC,
+                B_A = 2 * TC_MAX_STAGES + 2 * TC_ACC;
 
   if (tid == 0) {
-    for (int b = 0; b < TC_STAGES; ++b) {
+    for (int b = 0; b < TC_MAX_STAGES; ++b) {
       mbar_init(BAR(B_FULL + b), 1);
       mbar_init(BAR(B_EMPTY + b), 1);
+    }
+    for (int b = 0; b < TC_ACC; ++b) {
       mbar_init(BAR(B_TFULL + b), 1);
       mbar_init(BAR(B_TEMPTY + b), 8);
     }
@@ -442,11 +447,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
     // reference tiles are visited outwards from the tile that holds this query tile's first cell
     const int ctile = a.inv[a.qorder[(size_t)qt * TC_M]] / TC_N;
     // ring position of this query tile's first reference tile (stage ring and accumulator ring move together)
-    uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+    uint32_t s = it % NS, ph = (it / NS) & 1u;            // shared-memory stage ring
+    uint32_t b = it % TC_ACC, bph = (it / TC_ACC) & 1u;   // accumulator ring
     auto advance = [&]() {
-      if (++s == TC_STAGES) {
+      if (++s == NS) {
         s = 0;
         ph ^= 1u;
+      }
+      if (++b == TC_ACC) {
+        b = 0;
+        bph ^= 1u;
       }
     };
     // Producer and MMA warps run their loops warp-uniformly and elect one lane only around the asynchronous
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
       bool pre_ok = false;  // barriers of this tile were already seen complete while the previous tile was issued
       for (int rt = 0; ok && rt < a.n_r_tiles; ++rt, advance()) {
         if (!pre_ok) {
-          ok = mbar_wait(BAR(B_TEMPTY + s), ph ^ 1u, abort_flag);           // accumulator drained by the epilogue
+          ok = mbar_wait(BAR(B_TEMPTY + b), bph ^ 1u, abort_flag);          // accumulator drained by the epilogue
           if (leader) TC_TRACE(1);
           ok = ok && mbar_wait(BAR(B_FULL + s), ph, abort_flag);            // reference tile landed
           if (leader) TC_TRACE(2);
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         tc_fence_after();
         const uint32_t sb = smem_u32(sB) + s * tile_bytes;
         const uint64_t dB_hi = make_desc(sb), dB_lo = make_desc(sb + part_bytes);
-        const uint32_t dtm = tmem_base + s * (uint32_t)TC_N;
+        const uint32_t dtm = tmem_base + b * (uint32_t)TC_N;
         // per K step (16 halves): A advances 8 TMEM columns, B by 2 chunks = 2 * LBO = 4096 B = 256 descriptor units
         if (leader) {
           for (int k = 0; k < ksteps; ++k) tc_mma_f16_ts(dtm, tA_lo + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, k > 0);
@@ -502,14 +512,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         // still has work queued, so that the hand-over between tiles does not drain it
         pre_ok = false;
         if (rt + 1 < a.n_r_tiles) {
-          const uint32_t s1 = (s + 1 == TC_STAGES) ? 0u : s + 1u, ph1 = (s + 1 == TC_STAGES) ? (ph ^ 1u) : ph;
-          pre_ok = mbar_test(BAR(B_TEMPTY + s1), ph1 ^ 1u) && mbar_test(BAR(B_FULL + s1), ph1);
+          const uint32_t s1 = (s + 1 == NS) ? 0u : s + 1u, ph1 = (s + 1 == NS) ? (ph ^ 1u) : ph;
+          const uint32_t b1 = (b + 1 == TC_ACC) ? 0u : b + 1u, bph1 = (b + 1 == TC_ACC) ? (bph ^ 1u) : bph;
+          pre_ok = mbar_test(BAR(B_TEMPTY + b1), bph1 ^ 1u) && mbar_test(BAR(B_FULL + s1), ph1);
           pre_ok = __all_sync(FULLMASK, pre_ok);
         }
         if (leader) {
           for (int k = 0; k < ksteps; ++k) tc_mma_f16_ts(dtm, tA_hi + (uint32_t)(k * 8), dB_hi + (uint64_t)(k * 256), TC_IDESC, 1u);
           tc_commit(BAR(B_EMPTY + s));  // shared-memory stage free once these MMAs have read it
-          tc_commit(BAR(B_TFULL + s));  // accumulator ready for the epilogue
+          tc_commit(BAR(B_TFULL + b));  // accumulator ready for the epilogue
           TC_TRACE(3);
         }
         __syncwarp();
@@ -612,13 +623,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
         }
       };
       for (int rt = 0; rt < a.n_r_tiles; ++rt, advance()) {
-        ok = mbar_wait(BAR(B_TFULL + s), ph, abort_flag);
+        ok = mbar_wait(BAR(B_TFULL + b), bph, abort_flag);
         ok = __all_sync(FULLMASK, ok);
         if (!ok) break;
         if (warp == 4 && lane == 0) TC_TRACE(4);
         tc_fence_after();
         thr = fmaxf(thr, sthr[(1 - h) * TC_M + row_in_tile]);  // the other half's threshold is valid for this half too
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + s * (uint32_t)TC_N + (uint32_t)(h * 64);
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)TC_N + (uint32_t)(h * 64);
         const int colt = tile_seq(rt, ctile, a.n_r_tiles) * TC_N + h * 64;
         {
           // the tensor-memory load of the second chunk is in flight while the first one is scanned
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
           // everything this warp needs of the accumulator buffer is in registers: hand it back before the last scan
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_TEMPTY + s));
+          if (lane == 0) mbar_arrive(BAR(B_TEMPTY + b));
           scan_chunk(vb, colt + 32);
         }
         if (warp == 4 && lane == 0) TC_TRACE(5);
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn_filter_tc(TcArgs a) {
 static inline int knn_tc_kp(int d) { return ((d + 1 + 15) / 16) * 16; }
 
 bool sc_knn_tc_supported(int n, int d) {
-  return knn_tc_kp(d) <= 128 && n >= 2048;  // 3 stages of KP/2 KB + barriers fit the 227 KB of shared memory, A fits TMEM
+  return knn_tc_kp(d) <= 128 && n >= 2048;  // >= 3 stages of KP/2 KB + barriers fit the 227 KB of shared memory, A fits TMEM
 }
 
 // Error bound of the filter, as a multiple of (||xi|| + ||xj||)^2, for |(||xi||^2 - 2 s_computed) - ||xi - xj||^2|:
@@ -790,7 +801,10 @@ int sc_knn_filter_tc(sc_ctx* ctx, const float* Xc, const float* norm2, const flo
     a.trace = trace.p;
     a.trace_off = getenv("SC_KNN_TC_TRACE_OFF") ? atoi(getenv("SC_KNN_TC_TRACE_OFF")) : 0;
   }
-  const size_t smem = TC_STAGES * tile_bytes + 128 + 4 * TC_M * sizeof(float);
+  int stages = (int)((size_t)(200 * 1024) / tile_bytes);
+  stages = stages < 2 ? 2 : (stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages);
+  a.stages = stages;
+  const size_t smem = (size_t)stages * tile_bytes + 256 + 4 * TC_M * sizeof(float);
   SC_CUDA(ctx, cudaFuncSetAttribute(k_knn_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   SC_CUDA(ctx, cudaEventCreate(&e0));

@@ -705,3 +705,7 @@ def SEACells(ad, build_kernel_on: str, n_SEACells: int, use_gpu: bool = False, v
         assert not use_gpu, "Sparse matrix operations are only supported for CPU implementation."
     return SEACellsB200(ad, build_kernel_on, n_SEACells, verbose, n_waypoint_eigs, n_neighbors, convergence_epsilon,
                         l2_penalty, max_franke_wolfe_iters, use_sparse=use_sparse)
+
+
+# SEACells.core also hosts the metacell summaries (core.py:103-242); keep `from seacells_b200.core import ...` working
+from .summarize import sparsify_assignments, summarize_by_SEACell, summarize_by_soft_SEACell  # noqa: E402,F401

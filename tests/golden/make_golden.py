@@ -41,29 +41,29 @@ def _quiet(fn, *a, **k):
 
 
 def make_case(name, n, d, k, kind="rna", key="X_pca", dense=False, l2=0.0, max_iter=30, min_iter=10,
-              eps=1e-3, T=50, seed=0, with_greedy=False):
+              eps=1e-3, T=50, seed=0, with_greedy=False, nn=15):
     cpu = ref_shim.load("cpu")
     cpu_dense = ref_shim.load("cpu_dense")
     bg = ref_shim.load("build_graph")
     X32 = synth_embedding(n, d, seed, kind)
     X = X32.astype(np.float64)  # identical values; the reference then computes rbf in fp64
-    out = {"X32": X32, "n_neighbors": np.int64(15), "k": np.int64(k), "max_iter": np.int64(max_iter),
+    out = {"X32": X32, "n_neighbors": np.int64(nn), "k": np.int64(k), "max_iter": np.int64(max_iter),
            "min_iter": np.int64(min_iter), "eps": np.float64(eps), "T": np.int64(T), "l2": np.float64(l2),
            "dense": np.bool_(dense)}
 
     ad = MiniAnnData(X, key)
     cls = cpu_dense.SEACellsCPUDense if dense else cpu.SEACellsCPU
-    model = _quiet(cls, ad, key, k, False, 10, 15, eps, l2, T)
+    model = _quiet(cls, ad, key, k, False, 10, nn, eps, l2, T)
     _quiet(model.construct_kernel_matrix)
     D = ad.obsp["distances"]
     out.update(_csr_parts("D", D))
-    sig = np.array([bg.kth_neighbor_distance(D, 15 // 2, i) for i in range(n)])
+    sig = np.array([bg.kth_neighbor_distance(D, nn // 2, i) for i in range(n)])
     out["sigma"] = sig
     out.update(_csr_parts("M", model.kernel_matrix))
 
     ad2 = MiniAnnData(X, key)
     g2 = bg.SEACellGraph(ad2, key, verbose=False)
-    out.update(_csr_parts("Mint", _quiet(g2.rbf, 15, graph_construction="intersection")))
+    out.update(_csr_parts("Mint", _quiet(g2.rbf, nn, graph_construction="intersection")))
 
     arch = synth_archetypes(n, k)
     A0 = synth_assignments(n, k)
@@ -121,3 +121,5 @@ if __name__ == "__main__":
     make_case("rna_n600_k8_dense_l2", 600, 50, 8, dense=True, l2=0.05)
     make_case("atac_n900_k12_sparse", 900, 30, 12, kind="atac", key="X_svd")
     make_case("rna_n2000_k27_sparse", 2000, 50, 27)
+    # CPU-only extra (pins the oracle away from the defaults): 10 neighbours, 20 Frank-Wolfe steps, tighter epsilon
+    make_case("rna_n500_k9_nn10_T20", 500, 50, 9, nn=10, T=20, eps=1e-4, seed=5)

@@ -6,6 +6,8 @@ import scipy.sparse as sp
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["rna_n600_k8_sparse", "rna_n600_k8_dense_l2", "atac_n900_k12_sparse", "rna_n2000_k27_sparse"]
+# pins the oracle away from the default parameters (10 neighbours, 20 Frank-Wolfe steps); oracle tests only
+ORACLE_ONLY_CASES = ["rna_n500_k9_nn10_T20"]
 
 
 def load_golden(name):

@@ -4,10 +4,10 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import seacells_oracle as O
-from tests.helpers import CASES, csr_from, load_golden, same_sparse
+from tests.helpers import CASES, ORACLE_ONLY_CASES, csr_from, load_golden, same_sparse
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY_CASES)
 def test_kernel_build_matches_reference(name):
     g = load_golden(name)
     X = g["X32"].astype(np.float64)
@@ -23,7 +23,7 @@ def test_kernel_build_matches_reference(name):
         O.symmetrise(D, "bogus")
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ORACLE_ONLY_CASES)
 def test_fit_matches_reference(name):
     g = load_golden(name)
     M = csr_from(g, "M")

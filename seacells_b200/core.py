@@ -120,9 +120,15 @@ def spmm_csr(S: sp.csr_matrix, X: np.ndarray, ctx=None) -> np.ndarray:
 class FitEngine:
     """Device-resident model state (sc_fit): compressed A (k x n) and B (n x k)."""
 
+    MAX_FW_ITER = 64    # FW_SMAX in csrc/fit_kernels.cuh: slots per column of the compressed A / B
+    MAX_NEIGHBORS = 33  # shortlist width of the kNN kernels (csrc/kernel_build.cu) + 1
+
     def __init__(self, n, k, max_FW_iter=50, ctx=None):
         self.ctx = ctx or _lib.default_context()
         self.n, self.k, self.T = int(n), int(k), int(max_FW_iter)
+        if not 1 <= self.T <= self.MAX_FW_ITER:
+            raise ValueError(f"max_franke_wolfe_iters must be in [1, {self.MAX_FW_ITER}] for the B200 engine "
+                             f"(got {self.T}); see INTEGRATION.md, 'Capacity limits'")
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.sc_fit_create(self.ctx.h, self.n, self.k, self.T, C.byref(h)), "sc_fit_create")
         self.h = h
@@ -138,6 +144,8 @@ class FitEngine:
         if not M.has_sorted_indices:
             M = M.copy()
             M.sort_indices()
+        if M.nnz >= 2 ** 31:
+            raise ValueError(f"kernel matrix has {M.nnz} stored entries; the engine indexes them with int32 (< 2^31)")
         indptr = M.indptr.astype(np.int32)
         indices = M.indices.astype(np.int32)
         data = np.ascontiguousarray(M.data, np.float64)
@@ -210,7 +218,10 @@ class FitEngine:
         """initialize + _fit loop entirely inside the library.  Returns (rss_iters, n_iter, converged, threshold)."""
         thr = C.c_double(threshold if threshold is not None else -1.0)
         n_iter, conv, n_rss = C.c_int(0), C.c_int(0), C.c_int(0)
-        cap = max_iter + 2
+        if max_iter < min_iter:
+            raise ValueError("The maximum number of iterations specified is lower than the minimum number of "
+                             "iterations specified.")
+        cap = max(max_iter, min_iter) + 2
         rss = np.zeros(cap, np.float64)
         self.ctx.check(self.ctx.lib.sc_fit_run(self.h, int(max_iter), int(min_iter), float(eps), float(l2_penalty),
                                                C.byref(thr), C.byref(n_iter), C.byref(conv), ptr(rss), cap,
@@ -327,6 +338,13 @@ class SEACellsB200:
                 raise ValueError(
                     f"The number of SEACells specified must be an integer type, not {type(n_SEACells)}")
         self.k = n_SEACells
+        # capacity limits of the compiled kernels (the reference has none): fail here, not deep inside fit()
+        if not 1 <= int(max_franke_wolfe_iters) <= FitEngine.MAX_FW_ITER:
+            raise ValueError(f"max_franke_wolfe_iters must be in [1, {FitEngine.MAX_FW_ITER}] for the B200 engine, "
+                             f"not {max_franke_wolfe_iters} (INTEGRATION.md, 'Capacity limits')")
+        if not 2 <= int(n_neighbors) <= FitEngine.MAX_NEIGHBORS:
+            raise ValueError(f"n_neighbors must be in [2, {FitEngine.MAX_NEIGHBORS}] for the B200 engine, "
+                             f"not {n_neighbors} (INTEGRATION.md, 'Capacity limits')")
         self.n_waypoint_eigs = n_waypoint_eigs
         self.waypoint_proportion = 1
         self.n_neighbors = n_neighbors
@@ -341,6 +359,7 @@ class SEACellsB200:
         self.A0 = None
         self.B0 = None
         self.Z_ = None
+        self._device = device
         self._ctx = _lib.default_context(device)  # raises when the library or the GPU is missing
         self._km = None          # KernelMatrix (device) when built by construct_kernel_matrix
         self._M_host = None      # scipy CSR when given by add_precomputed_kernel_matrix / exported
@@ -363,6 +382,7 @@ class SEACellsB200:
         self._km = None
         self._K_host = None
         self._engine = None
+        self._A_cache = self._B_cache = None
 
     @property
     def K(self):
@@ -388,6 +408,7 @@ class SEACellsB200:
         print(f"Parameter graph_construction = {graph_construction} being used to build KNN graph...")
         km = build_kernel(X, n_neighbors, graph_construction, self._ctx)
         self._km, self._M_host, self._K_host, self._engine = km, None, None, None
+        self._A_cache = self._B_cache = None
         if hasattr(self.ad, "obsp"):
             M, self.sigma_, idx, d2 = km.export(want_knn=True)
             self._M_host = M
@@ -449,6 +470,8 @@ class SEACellsB200:
         if self._engine is None or self._engine.k != k or self._engine.T != self.max_FW_iter:
             if self._km is None and self._M_host is None:
                 raise RuntimeError("Must first construct kernel matrix before initializing SEACells.")
+            if self._ctx is None:  # restored from a pickle
+                self._ctx = _lib.default_context(getattr(self, "_device", 0))
             eng = FitEngine(self.n_cells, k, self.max_FW_iter, self._ctx)
             eng.set_kernel(self._km if self._km is not None else self._M_host)
             self._engine = eng
@@ -507,21 +530,34 @@ class SEACellsB200:
     # ---- model state as the reference exposes it ---------------------------------------------------------------
     @property
     def A_(self):
-        if self._engine is None:
-            return None
-        if self._A_cache is None:
+        if self._A_cache is None and self._engine is not None:
             A = self._engine.A()
             self._A_cache = A if self.use_sparse else A.toarray()
         return self._A_cache
 
     @property
     def B_(self):
-        if self._engine is None:
-            return None
-        if self._B_cache is None:
+        if self._B_cache is None and self._engine is not None:
             B = self._engine.B()
             self._B_cache = B if self.use_sparse else B.toarray()
         return self._B_cache
+
+    def _fitted_engine(self):
+        """The engine holding A_ / B_.  A model restored from a pickle (save_model) has host matrices only: the device
+        state is rebuilt from them on first use."""
+        if self._engine is None:
+            if self._A_cache is None or self._B_cache is None:
+                raise RuntimeError("Cell to SEACell assignment matrix has not been initialised. "
+                                   "Run model.initialize() first.")
+            if self._ctx is None:
+                self._ctx = _lib.default_context(getattr(self, "_device", 0))
+            A, B = sp.csc_matrix(self._A_cache), sp.csr_matrix(self._B_cache)
+            eng = FitEngine(self.n_cells, A.shape[0], self.max_FW_iter, self._ctx)
+            eng.set_kernel(self._M_host)
+            eng.set_A_compressed(A)
+            eng.set_B(B)
+            self._engine = eng
+        return self._engine
 
     def _updateA(self, B, A_prev):
         """cpu.py:425-459 for explicit matrices (k x n A_prev, n x k B with compressible columns)."""
@@ -554,9 +590,9 @@ class SEACellsB200:
     def compute_RSS(self, A=None, B=None):
         """cpu.py:520-536: ||M - (M B) A||_F, evaluated on the GPU without the n x n product."""
         if A is None and B is None:
-            if self._engine is None:
+            if self._engine is None and self._A_cache is None:
                 raise RuntimeError("Either assignment matrix A or archetype matrix B is None.")
-            return self._engine.rss()
+            return self._fitted_engine().rss()
         A = self.A_ if A is None else A
         B = self.B_ if B is None else B
         if A is None or B is None:
@@ -594,9 +630,10 @@ class SEACellsB200:
         """cpu.py:558-593."""
         if self._km is None and self._M_host is None:
             raise RuntimeError("Kernel matrix has not been computed. Run model.construct_kernel_matrix() first.")
-        if self._engine is None:
+        if self._engine is None and self._A_cache is None:
             raise RuntimeError(
                 "Cell to SEACell assignment matrix has not been initialised. Run model.initialize() first.")
+        self._fitted_engine()
         self._step_engine()
         labels = self.get_hard_assignments()
         self.ad.obs["SEACell"] = labels["SEACell"]
@@ -639,14 +676,14 @@ class SEACellsB200:
 
     def get_archetype_matrix(self):
         """cpu.py:680-682: Z_ = B_.T @ K (k x n)."""
-        if self.Z_ is None and self._engine is not None:
-            Z = self._engine.KB().T.tocsc()   # (K B)^T = B^T K since K is symmetric; computed on the GPU
+        if self.Z_ is None and (self._engine is not None or self._A_cache is not None):
+            Z = self._fitted_engine().KB().T.tocsc()   # (K B)^T = B^T K since K is symmetric; computed on the GPU
             self.Z_ = Z if self.use_sparse else Z.toarray()
         return self.Z_
 
     def get_soft_assignments(self):
         """cpu_dense.py:586-605 (the well-formed definition): top-5 (label, weight) per cell."""
-        idx, w = self._engine.soft_assignments(5)
+        idx, w = self._fitted_engine().soft_assignments(5)
         arch = self.get_hard_archetypes()
         soft_labels = pd.DataFrame(np.asarray(arch)[idx])
         soft_labels.index = self.ad.obs_names
@@ -654,7 +691,7 @@ class SEACellsB200:
 
     def get_hard_assignments(self):
         """cpu.py:710-722."""
-        assmts = self._engine.hard_assignments()
+        assmts = self._fitted_engine().hard_assignments()
         df = pd.DataFrame({"SEACell": [f"SEACell-{i}" for i in assmts]})
         df.index = self.ad.obs_names
         df.index.name = "index"
@@ -662,7 +699,7 @@ class SEACellsB200:
 
     def get_hard_archetypes(self):
         """cpu.py:724-729."""
-        return self.ad.obs_names[self._engine.hard_archetypes()]
+        return self.ad.obs_names[self._fitted_engine().hard_archetypes()]
 
     def save_model(self, outdir):
         """cpu.py:731-741 (the device handles are dropped from the pickle; host state is kept)."""
@@ -672,12 +709,19 @@ class SEACellsB200:
         return None
 
     def __getstate__(self):
+        # the reference pickles A_, B_, Z_, kernel_matrix with the model (cpu.py:731-741): materialise them on the host
+        fitted = self._engine is not None or self._A_cache is not None
         st = dict(self.__dict__)
         st["_A_cache"], st["_B_cache"] = self.A_, self.B_
+        st["Z_"] = self.get_archetype_matrix() if fitted and getattr(self, "_fitted", False) else self.Z_
         st["_M_host"] = self.kernel_matrix
+        st["_K_host"] = None  # K = M @ M.T is recomputed on access
         for key in ("_ctx", "_km", "_engine"):
             st[key] = None
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)  # device handles are re-created lazily (_fitted_engine / _ensure_engine)
 
     def save_assignments(self, outdir):
         """cpu.py:743-764: SEACells.csv, kernel_matrix.npz, A.npz (= A_.T, n x k), B.npz."""

@@ -94,7 +94,8 @@ int sc_ctx_create(int device, sc_ctx** out) {
     cudaGetLastError();
     return SC_ERR_CUDA;  // no usable CUDA device: there is no CPU fallback
   }
-  if (cudaSetDevice(device) != cudaSuccess) return SC_ERR_CUDA;
+  DeviceGuard dev_guard(device);
+  if (dev_guard.prev != device && !dev_guard.switched) return SC_ERR_CUDA;
   sc_ctx* c = new (std::nothrow) sc_ctx();
   if (!c) return SC_ERR_CUDA;
   c->device = device;
@@ -108,6 +109,7 @@ int sc_ctx_create(int device, sc_ctx** out) {
 
 void sc_ctx_destroy(sc_ctx* ctx) {
   if (!ctx) return;
+  DeviceGuard dev_guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -127,6 +129,8 @@ int sc_knn_profile(sc_ctx* ctx, double* out4) {
 void* sc_stream(sc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int sc_sync(sc_ctx* ctx) {
+  if (!ctx) return SC_ERR_ARG;
+  DeviceGuard dev_guard(ctx->device);
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SC_OK;
 }
@@ -135,7 +139,7 @@ int sc_sync(sc_ctx* ctx) {
 int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbors, int row_begin, int row_end,
            int32_t* idx_out, double* d2_out) {
   if (!ctx || !X || !idx_out || !d2_out || n <= 0 || d <= 0) return SC_ERR_ARG;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   const size_t esz = x_is_f64 ? 8 : 4;
   DBuf<char> xs;
   const char* Xd = nullptr;
@@ -165,7 +169,7 @@ int sc_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int n_neighbo
 int sc_knn_tc_probe(sc_ctx* ctx, const void* X, int x_is_f64, int n, int d, int cols, float* s_out, float* xc_out,
                     float* norm2_out) {
   if (!ctx || !X || !s_out || !xc_out || !norm2_out || n <= 0 || d <= 0 || cols <= 0) return SC_ERR_ARG;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   const size_t esz = x_is_f64 ? 8 : 4;
   DBuf<char> xs;
   const char* Xd = nullptr;
@@ -190,7 +194,7 @@ int sc_summarize(sc_ctx* ctx, int n, int n_genes, const int64_t* indptr, const i
                  int n_groups, const double* divisor, double* out) {
   if (!ctx || !indptr || !out || n <= 0 || n_genes <= 0 || n_groups <= 0 || m < 0) return SC_ERR_ARG;
   if (m > 0 && (!group || !cell || !weight || !indices || !data)) return SC_ERR_ARG;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   long long nnz = 0;
   {
     // indptr may be on the host or on the device
@@ -233,7 +237,7 @@ static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, in
                              long long* nnz_out) {
   if (!ctx || !X || !out || n <= 0 || d <= 0) return SC_ERR_ARG;
   if (intersection != 0 && intersection != 1) SC_FAIL(ctx, SC_ERR_ARG, "graph_construction must be union or intersection");
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   *out = nullptr;
   const size_t esz = x_is_f64 ? 8 : 4;
   DBuf<char> xs;
@@ -282,6 +286,7 @@ int sc_kernel_build_from_knn(sc_ctx* ctx, const void* X, int x_is_f64, int n, in
 int sc_kernel_export(sc_ctx* ctx, sc_kernel* km, int32_t* indptr, int32_t* indices, double* data, double* sigma,
                      int32_t* knn_idx, double* knn_d2) {
   if (!ctx || !km) return SC_ERR_ARG;
+  DeviceGuard dev_guard(ctx->device);
   const size_t n = km->n, nnz = km->nnz, kk = km->kk;
   if (indptr) SC_CUDA(ctx, sc_copy(indptr, km->indptr.p, sizeof(int) * (n + 1), ctx->stream));
   if (indices) SC_CUDA(ctx, sc_copy(indices, km->indices.p, sizeof(int) * nnz, ctx->stream));
@@ -298,7 +303,7 @@ void sc_kernel_free(sc_kernel* km) { delete km; }
 int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, const int32_t* indices,
                     const double* data, const double* X, double* Y) {
   if (!ctx || r <= 0 || m <= 0 || c <= 0 || !indptr || !indices || !data || !X || !Y) return SC_ERR_ARG;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   int h_nnz = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, indptr + r, sizeof(int), cudaMemcpyDefault, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -327,7 +332,7 @@ int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, con
 int sc_greedy_centers(sc_ctx* ctx, int n, const int32_t* indptr, const int32_t* indices, const double* data,
                       long long nnz, int n_centers, int64_t* centers_out) {
   if (!ctx || !indptr || !indices || !data || !centers_out) return SC_ERR_ARG;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   return sc_greedy_centers_impl(ctx, n, indptr, indices, data, nnz, n_centers, (long long*)centers_out);
 }
 
@@ -335,7 +340,7 @@ int sc_greedy_centers(sc_ctx* ctx, int n, const int32_t* indptr, const int32_t* 
 int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out) {
   if (!ctx || !out) return SC_ERR_ARG;
   *out = nullptr;
-  SC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   sc_fit* f = new (std::nothrow) sc_fit();
   if (!f) SC_FAIL(ctx, SC_ERR_CUDA, "out of host memory");
   int rc = f->init(ctx, n_cells, n_archetypes, max_FW_iter);
@@ -350,38 +355,45 @@ int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, s
 
 void sc_fit_destroy(sc_fit* fit) {
   if (!fit) return;
+  DeviceGuard dev_guard(fit->ctx->device);
   cudaStreamSynchronize(fit->ctx->stream);
   delete fit;
 }
 
 int sc_fit_set_kernel(sc_fit* fit, const int32_t* indptr, const int32_t* indices, const double* data, long long nnz) {
   if (!fit || !indptr || !indices || !data || nnz <= 0) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_kernel(indptr, indices, data, nnz);
 }
 
 int sc_fit_set_kernel_from(sc_fit* fit, sc_kernel* km) {
   if (!fit || !km) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   if (km->n != fit->n) SC_FAIL(fit->ctx, SC_ERR_ARG, "kernel matrix dimension does not match n_cells");
   return fit->set_kernel(km->indptr.p, km->indices.p, km->data.p, km->nnz);
 }
 
 int sc_fit_set_archetypes(sc_fit* fit, const int64_t* cell_positions) {
   if (!fit || !cell_positions) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_B_onehot((const long long*)cell_positions);
 }
 
 int sc_fit_set_A_csc(sc_fit* fit, const int64_t* colptr, const int32_t* rows, const double* vals) {
   if (!fit || !colptr || !rows || !vals) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_A_lists((const long long*)colptr, rows, vals);
 }
 
 int sc_fit_set_A_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_A_slots(idx, val, cnt);
 }
 
 int sc_fit_set_B_slots(sc_fit* fit, const int32_t* idx, const double* val, const int32_t* cnt) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_B_slots(idx, val, cnt);
 }
 
@@ -402,22 +414,26 @@ static int with_trace(sc_fit* fit, int32_t* trace, size_t count, int (*fn)(sc_fi
 
 int sc_fit_update_A(sc_fit* fit, double l2_penalty, int32_t* trace) {
   if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return with_trace(fit, trace, (size_t)fit->T * fit->n,
                     [](sc_fit* f, int* t, double l2) { return f->update_A(l2, t); }, l2_penalty);
 }
 
 int sc_fit_update_B(sc_fit* fit, int32_t* trace) {
   if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return with_trace(fit, trace, (size_t)fit->T * fit->k, [](sc_fit* f, int* t, double) { return f->update_B(t); }, 0.0);
 }
 
 int sc_fit_set_shard(sc_fit* fit, int row_begin, int row_end) {
   if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->set_shard(row_begin, row_end);
 }
 
 int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long long* rows_allocated) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   if (!fit->have_A || !fit->a_is_slots) SC_FAIL(fit->ctx, SC_ERR_STATE, "fit: A has not been computed");
   *idx = fit->a_idx[fit->a_cur].p;
   *val = fit->a_val[fit->a_cur].p;
@@ -426,21 +442,32 @@ int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long 
   return SC_OK;
 }
 
-int sc_fit_update_B_begin(sc_fit* fit) { return fit ? fit->update_B_begin() : SC_ERR_ARG; }
+int sc_fit_update_B_begin(sc_fit* fit) {
+  if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
+  return fit->update_B_begin();
+}
 int sc_fit_update_B_eval(sc_fit* fit, int t, double* partial_dev) {
   if (!fit || !partial_dev) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   if (!sc_is_device_ptr(partial_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_eval: partial buffer must be device memory");
   return fit->update_B_eval(t, partial_dev);
 }
 int sc_fit_update_B_step(sc_fit* fit, int t, const double* gathered_dev, int n_ranks) {
   if (!fit || !gathered_dev || n_ranks < 1) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   if (!sc_is_device_ptr(gathered_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_step: gathered buffer must be device memory");
   return fit->update_B_step(t, gathered_dev, n_ranks, nullptr);
 }
-int sc_fit_update_B_end(sc_fit* fit) { return fit ? fit->update_B_end() : SC_ERR_ARG; }
+int sc_fit_update_B_end(sc_fit* fit) {
+  if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
+  return fit->update_B_end();
+}
 
 int sc_fit_rss(sc_fit* fit, double* rss_out) {
   if (!fit || !rss_out) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->rss(rss_out);
 }
 
@@ -448,6 +475,7 @@ int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsil
                double* threshold_inout, int* n_iter_out, int* converged_out, double* rss_out, int rss_cap,
                int* n_rss_out) {
   if (!fit || !threshold_inout || !n_iter_out || !converged_out || !rss_out || !n_rss_out) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   if (max_iter < min_iter) SC_FAIL(fit->ctx, SC_ERR_ARG, "max_iter < min_iter");
   return fit->run(max_iter, min_iter, convergence_epsilon, l2_penalty, threshold_inout, n_iter_out, converged_out,
                   rss_out, rss_cap, n_rss_out);
@@ -455,27 +483,33 @@ int sc_fit_run(sc_fit* fit, int max_iter, int min_iter, double convergence_epsil
 
 int sc_fit_get_KB(sc_fit* fit, long long* nnz_out, int64_t* indptr, int32_t* indices, double* data) {
   if (!fit) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->get_KB_csr(nnz_out, (long long*)indptr, indices, data);
 }
 int sc_fit_slots(sc_fit* fit) { return fit ? fit->S : 0; }
 int sc_fit_get_A(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->get_A(idx, val, cnt);
 }
 int sc_fit_get_B(sc_fit* fit, int32_t* idx, double* val, int32_t* cnt) {
   if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->get_B(idx, val, cnt);
 }
 int sc_fit_hard_assignments(sc_fit* fit, int32_t* labels) {
   if (!fit || !labels) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->hard_assignments(labels);
 }
 int sc_fit_hard_archetypes(sc_fit* fit, int32_t* cells) {
   if (!fit || !cells) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->hard_archetypes(cells);
 }
 int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w) {
   if (!fit || !idx || !w) return SC_ERR_ARG;
+  DeviceGuard dev_guard(fit->ctx->device);
   return fit->soft_assignments(top, idx, w);
 }
 int sc_fit_stats(sc_fit* fit, long long* out4) {

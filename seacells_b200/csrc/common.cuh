@@ -57,6 +57,22 @@ struct sc_ctx {
     return (code);              \
   } while (0)
 
+// Makes the context's device current for the duration of an extern "C" call and restores the caller's device on exit
+// (the caller - torch, another model on another GPU - may have switched devices between calls).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // kernel launch + bookkeeping (+ immediate launch-error check)
 #define SC_LAUNCH(ctx, kern, grid, block, smem, ...)                        \
   do {                                                                      \

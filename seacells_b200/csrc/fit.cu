@@ -40,6 +40,37 @@ __global__ void k_square(const double* __restrict__ in, double* __restrict__ out
   if (i < n) out[i] = in[i] * in[i];
 }
 
+// Input validation.  K = M M^T (cpu.py:128,157) is applied as M (M .) and the RSS uses the same products, which is only
+// the reference's arithmetic when M equals its transpose; the candidate restriction needs M, A0 >= 0.  flag bit 0: a
+// negative or NaN value, bit 1: M[i,j] has no equal M[j,i].
+__global__ void k_check_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+                               const double* __restrict__ val, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int bad = 0;
+  for (int e = ptr[i]; e < ptr[i + 1]; ++e) {
+    const int j = col[e];
+    const double v = val[e];
+    if (!(v >= 0.0)) bad |= 1;
+    if (j < 0 || j >= n) {
+      bad |= 2;
+      continue;
+    }
+    int lo = ptr[j], hi = ptr[j + 1];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (col[mid] < i) lo = mid + 1;
+      else hi = mid;
+    }
+    if (!(lo < ptr[j + 1] && col[lo] == i && val[lo] == v)) bad |= 2;
+  }
+  if (bad) atomicOr(flag, bad);
+}
+__global__ void k_check_nonneg(size_t count, const double* __restrict__ val, int* __restrict__ flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count && !(val[i] >= 0.0)) atomicOr(flag, 1);
+}
+
 // B by cell: (cell, archetype) pairs -> radix sort -> row bounds.  Rows come out sorted by archetype.
 __global__ void k_emit_b_pairs(int k, int S, const int* __restrict__ b_idx, const double* __restrict__ b_val,
                                const int* __restrict__ b_cnt, const long long* __restrict__ off,
@@ -162,6 +193,9 @@ __device__ __forceinline__ int fwA_zero_scan(int k, const double* __restrict__ t
 // being re-summed over the active slots at every step (that re-summation was ~25 t1 gathers per archetype and step
 // for the zero scan alone: 320 KB of L2 traffic per cell and call).  Exact zeros stay exact: a sum of non-negative
 // terms is zero iff every term is.
+// RESUM = true (SC_FIT_RESUM_A=1) re-sums (t1 A) over the active slots at every step, in slot order, instead of advancing
+// the running products: the parity tests run both variants against the oracle's argmin traces.
+template <bool RESUM>
 __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,6 +264,20 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
     __syncwarp();
     // ---- t >= 1
     for (int t = 1; t < T; ++t) {
+      if (RESUM) {
+        for (int c = lane; c < nc; c += 32) {
+          double acc = 0.0;
+          const int id = ck[c];
+          for (int e = 0; e < nslots; ++e) acc = fma(t1T[(size_t)sid[e] * k + id], sa[e], acc);
+          Hc[c] = acc;
+        }
+        if (lane < k) {
+          double acc = 0.0;
+          for (int e = 0; e < nslots; ++e) acc = fma(t1T[(size_t)sid[e] * k + lane], sa[e], acc);
+          Hz[lane] = acc;
+        }
+        __syncwarp();
+      }
       bv = FW_INF;
       bi = 0x7fffffff;
       for (int c = lane; c < nc; c += 32) {
@@ -268,7 +316,7 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
         }
         nslots++;
       }
-      {
+      if (!RESUM) {
         const double* __restrict__ trow = t1T + (size_t)chosen * k;
         for (int c = lane; c < nc; c += 32) Hc[c] = fw_step(Hc[c], trow[ck[c]], gamma);
         if (lane < k) Hz[lane] = fw_step(Hz[lane], trow[lane], gamma);
@@ -1329,7 +1377,9 @@ void sc_fit::pstop(int stage) {
 static int set_smem_attr_once(sc_ctx* ctx) {
   static bool done = false;
   if (done) return SC_OK;
-  SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(FWA_PER_WARP * FWA_WARPS)));
+  SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(FWA_PER_WARP * FWA_WARPS)));
   done = true;
   return SC_OK;
@@ -1344,6 +1394,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
   profile = std::getenv("SC_PROFILE") != nullptr;
   fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
+  resum_A = std::getenv("SC_FIT_RESUM_A") != nullptr;
   if (const char* e = std::getenv("SC_HUB_MAX")) hub_cap = std::max(0, std::min(HUB_MAX, atoi(e)));
   n = n_;
   row_begin = 0;
@@ -1384,6 +1435,18 @@ int sc_fit::set_kernel(const int* indptr, const int* indices, const double* data
   SC_CUDA(ctx, sc_copy(m_col.p, indices, sizeof(int) * (size_t)nnz, ctx->stream));
   SC_CUDA(ctx, sc_copy(m_val.p, data, sizeof(double) * (size_t)nnz, ctx->stream));
   m_nnz = nnz;
+  {
+    SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
+    SC_LAUNCH(ctx, k_check_kernel, (n + 127) / 128, 128, 0, n, m_ptr.p, m_col.p, m_val.p, slow_cnt.p);
+    int flag = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&flag, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag & 1) SC_FAIL(ctx, SC_ERR_ARG, "kernel matrix has negative or NaN entries (the engine needs M >= 0)");
+    if (flag & 2)
+      SC_FAIL(ctx, SC_ERR_ARG,
+              "kernel matrix is not symmetric: the engine applies K = M M^T as M (M .), which equals the reference's "
+              "K only for M == M^T (every matrix SEACellGraph.rbf builds is)");
+  }
   // ||M||_F^2 (fixed-order reduction)
   DBuf<double> sq;
   SC_TRY(sq.ensure(ctx, (size_t)nnz));
@@ -1435,7 +1498,14 @@ int sc_fit::set_A_lists(const long long* colptr, const int* idx, const double* v
   SC_CUDA(ctx, sc_copy(a0.len.p, hl.data(), sizeof(int) * (size_t)n, ctx->stream));
   SC_CUDA(ctx, sc_copy(a0.key.p, idx, sizeof(int) * (size_t)nnz, ctx->stream));
   SC_CUDA(ctx, sc_copy(a0.val.p, val, sizeof(double) * (size_t)nnz, ctx->stream));
+  int flag = 0;
+  if (nnz > 0) {
+    SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
+    SC_LAUNCH(ctx, k_check_nonneg, (unsigned)((nnz + 255) / 256), 256, 0, (size_t)nnz, a0.val.p, slow_cnt.p);
+    SC_CUDA(ctx, cudaMemcpyAsync(&flag, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag) SC_FAIL(ctx, SC_ERR_ARG, "initial assignments must be non-negative");
   a0.rows = n;
   a_cur = -1;
   have_A = true;
@@ -1617,7 +1687,8 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   pstart();
   if (l2 == 0.0) {
     int grid = std::min((row_end - row_begin + FWA_WARPS - 1) / FWA_WARPS, 148 * 16);
-    SC_LAUNCH(ctx, k_updateA_fast, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
+    if (resum_A) SC_LAUNCH(ctx, k_updateA_fast<true>, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
+    else SC_LAUNCH(ctx, k_updateA_fast<false>, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
     SC_CUDA(ctx, cudaMemcpyAsync(&nslow, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   } else {

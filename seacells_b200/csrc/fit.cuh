@@ -39,6 +39,7 @@ struct sc_fit {
   RowListsBuf erow, EY, DKB, KB2;
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
+  bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step
   DBuf<long long> b_off;
   DBuf<unsigned long long> bk_in, bk_out;
   DBuf<double> bv_in;

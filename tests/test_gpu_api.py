@@ -139,3 +139,87 @@ def test_step_explicit_updates_and_persistence():
         model.save_model(d)                                           # cpu.py:731-741
         m2 = pickle.load(open(os.path.join(d, "model.pkl"), "rb"))
         assert m2.RSS_iters == model.RSS_iters and m2.k == k
+        # the pickle keeps the fitted state (cpu.py:731-741 pickles A_, B_, Z_ with the model)
+        assert same_sparse(m2.A_, model.A_) and same_sparse(m2.B_, model.B_)
+        assert same_sparse(m2.kernel_matrix, model.kernel_matrix)
+        assert list(m2.get_hard_assignments()["SEACell"]) == list(model.get_hard_assignments()["SEACell"])
+        assert list(m2.get_hard_archetypes()) == list(model.get_hard_archetypes())
+        s2, w2 = m2.get_soft_assignments()
+        s1, w1 = model.get_soft_assignments()
+        assert np.array_equal(w1, w2) and s1.equals(s2)
+        np.testing.assert_allclose(m2.compute_RSS(), model.compute_RSS(), rtol=1e-12)
+        m2.step()                                                     # a restored model resumes like the original
+        model.step()
+        assert same_sparse(m2.A_, model.A_) and same_sparse(m2.B_, model.B_)
+
+
+def test_pickle_keeps_Z_after_fit():
+    import pickle
+    from seacells_b200 import SEACells
+    from seacells_b200.synth import MiniAnnData, synth_archetypes, synth_assignments
+    n, k = 700, 9
+    X, M = _data(n, seed=4)
+    model = SEACells(MiniAnnData(X), "X_pca", k, verbose=False, use_sparse=True)
+    model.add_precomputed_kernel_matrix(M)
+    try:
+        model.fit(max_iter=12, min_iter=3, initial_archetypes=synth_archetypes(n, k),
+                  initial_assignments=synth_assignments(n, k))
+    except RuntimeWarning:
+        pass                                           # raised after the results are stored (cpu.py:647-650)
+    m2 = pickle.loads(pickle.dumps(model))
+    assert m2._engine is None and m2.Z_ is not None
+    assert same_sparse(m2.Z_, model.get_archetype_matrix())
+    assert same_sparse(m2.A_, model.A_) and same_sparse(m2.B_, model.B_)
+
+
+def test_input_validation():
+    """Inputs the engine cannot treat like the reference are rejected loudly instead of mis-computed."""
+    from seacells_b200 import FitEngine, SEACells, SeacellsB200Error
+    from seacells_b200.synth import MiniAnnData, synth_archetypes, synth_assignments
+    n, k = 600, 8
+    X, M = _data(n, seed=6)
+    eng = FitEngine(n, k)
+    bad = sp.csr_matrix(M).copy().tolil()
+    bad[3, 5] = 0.25                                   # M[3,5] != M[5,3]: K = M M^T is no longer M (M .)
+    with pytest.raises(SeacellsB200Error, match="symmetric"):
+        eng.set_kernel(bad.tocsr())
+    neg = sp.csr_matrix(M).copy()
+    neg.data[7] = -neg.data[7]
+    with pytest.raises(SeacellsB200Error, match="negative"):
+        eng.set_kernel(neg)
+    eng.set_kernel(M)
+    eng.set_archetypes(synth_archetypes(n, k))
+    A0 = O.l1_normalise_columns(synth_assignments(n, k)).tocsc()
+    A0.data[0] = -0.5
+    with pytest.raises(SeacellsB200Error, match="non-negative"):
+        eng.set_A(A0)
+    ad = MiniAnnData(X)
+    with pytest.raises(ValueError, match="max_franke_wolfe_iters"):
+        SEACells(ad, "X_pca", k, verbose=False, max_franke_wolfe_iters=65)
+    with pytest.raises(ValueError, match="n_neighbors"):
+        SEACells(ad, "X_pca", k, verbose=False, n_neighbors=40)
+    with pytest.raises(ValueError):
+        eng.run(max_iter=3, min_iter=5)
+
+
+def test_two_devices_in_one_process():
+    """Every extern "C" entry point makes its context's device current (and restores the caller's)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from seacells_b200 import FitEngine, _lib
+    from seacells_b200.synth import synth_archetypes, synth_assignments
+    n, k = 900, 10
+    X, M = _data(n, seed=8)
+    arch, A0 = synth_archetypes(n, k), O.l1_normalise_columns(synth_assignments(n, k))
+    res = []
+    engines = [FitEngine(n, k, 50, _lib.default_context(dv)) for dv in (0, 1)]
+    for e in engines:
+        e.set_kernel(M); e.set_archetypes(arch); e.set_A(A0)
+    for step in range(2):
+        for dv, e in enumerate(engines):
+            torch.cuda.set_device(1 - dv)               # the caller's current device is the *other* GPU
+            e.update_A(); e.update_B()
+            assert torch.cuda.current_device() == 1 - dv
+    assert same_sparse(engines[0].A(), engines[1].A()) and same_sparse(engines[0].B(), engines[1].B())
+    assert engines[0].rss() == engines[1].rss()

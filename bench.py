@@ -65,7 +65,10 @@ def _knn_roofline(n, d, world, filter_s, kind, kp, fallback_rows):
                 peak, src = float(json.load(open(p))["bf16_tflops_sustained"]), "measured bf16_tflops_sustained"
             except Exception:
                 pass
-        out.update({"bound": "tensor", "executed_f16_tflops": ex, "peak": peak, "unit": "TFLOP/s", "frac": ex / peak,
+        out.update({"bound": "tensor", "executed_f16_tflops": ex, "peak": peak, "unit": "TFLOP/s",
+                    "frac_algorithmic": alg / peak, "frac_executed": ex / peak, "frac": alg / peak,
+                    "frac_note": "frac = algorithmic 2 n_q n d flops / peak (SURVEY.md 8d); frac_executed counts the 3 "
+                                 "split products over the padded K the tensor pipe actually ran",
                     "peak_source": src + " (fp16 and bf16 MMAs run at the same rate)"})
     return out
 
@@ -142,28 +145,69 @@ def cpu_fit_sample(n, seed=0):
     return dt, r["n_iter"], k
 
 
+def _cpu_replica(args):
+    n, seed, reps = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    from oracle import seacells_oracle as O
+    from seacells_b200.synth import synth_archetypes, synth_assignments, synth_embedding
+    k = max(2, n // 75)
+    X = synth_embedding(n, 50, seed).astype(np.float64)
+    M, *_ = O.build_kernel(X, 15)
+    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
+    ts, it = [], 0
+    for _ in range(reps):
+        t = time.perf_counter()
+        r = O.fit(M, arch, A0, max_iter=100, min_iter=10, convergence_epsilon=1e-3, max_FW_iter=50)
+        ts.append(time.perf_counter() - t)
+        it = r["n_iter"]
+    return ts, it, k
+
+
+def cpu_fit_replicas(n, procs, reps):
+    """`procs` independent fits of the same n-cell sample side by side (the reference's loop is single-threaded scipy, so
+    replicas are how it uses every host core); returns per-rep wall seconds (max over the replicas), iterations, k."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(_cpu_replica, [(n, 0, reps)] * procs)
+    per_rep = [max(r[0][i] for r in res) for i in range(reps)]
+    return per_rep, res[0][1], res[0][2]
+
+
+C1_CELLS, C1_K = 10_000, 133  # BASELINE.json configs[0]: the reference's own CPU-runnable case
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
     total = args.steps + args.warmup
     n = 4000 if total <= 4 else (2500 if total <= 8 else 1600)
-    for _ in range(args.warmup):
-        cpu_fit_sample(n)
-    ts, iters = [], 0
-    for _ in range(args.steps):
-        dt, iters, k = cpu_fit_sample(n)
-        ts.append(dt)
-    sec = float(np.mean(ts))
-    val = n / sec
-    sample = (f"full fit() (initialize + {iters} outer iterations, T=50) of the oracle restatement of cpu.SEACellsCPU on a "
-              f"{n}-cell x 50-PC sample (k={k}) of the workload; scipy sparse, single thread")
+    per_rep, iters, k = cpu_fit_replicas(n, procs, total)
+    sec = float(np.mean(per_rep[args.warmup:]))
+    val = procs * n / sec
+    sample = (f"{procs} independent replicas (one per host core, {cores} available) of a full fit() (initialize + {iters} "
+              f"outer iterations, T=50) of the oracle restatement of cpu.SEACellsCPU on a {n}-cell x 50-PC sample (k={k}) "
+              f"of the workload; scipy sparse, each replica single-threaded as the reference's loop is; value = "
+              f"replicas x cells / wall seconds")
+    # same-config pair (BASELINE config 1): ONE full 10k-cell fit per replica, untimed kernel construction
+    same = None
+    if not args.no_same_config:
+        c1_rep, c1_iters, c1_k = cpu_fit_replicas(C1_CELLS, min(procs, 8), 1)
+        same = {"config": f"config 1: synthetic {C1_CELLS} cells x 50 PCs, n_SEACells={c1_k}, full fit() "
+                          f"(initialize + {c1_iters} outer iterations)", "cpu_fit_s": c1_rep[0], "cpu_replicas": min(procs, 8),
+                "cpu_cells_per_s_one_fit": C1_CELLS / c1_rep[0],
+                "cpu_cells_per_s_all_replicas": min(procs, 8) * C1_CELLS / c1_rep[0], "kind": "port"}
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args.cells), "sample_cells": n},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                            "host_cores_available": os.cpu_count()},
+           "config": {"workload": workload_name(args.cells), "sample_cells": n, "same_config": False,
+                      "note": "the reference cannot run the 1M-cell configuration (SURVEY.md 6); see `same_config` for "
+                              "a pair measured on one configuration"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                            "host_cores_available": cores},
+           "same_config": same,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(out)
 
@@ -216,7 +260,8 @@ def run_ours(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_indptr, h_indices, h_data = pin(M.indptr.astype(np.int32)), pin(M.indices.astype(np.int32)), pin(M.data)
     arch = synth_archetypes(n, k)
-    A0 = normalize(synth_assignments(n, k), axis=0, norm="l1").tocsc()
+    A0_raw = synth_assignments(n, k)
+    A0 = normalize(A0_raw, axis=0, norm="l1").tocsc()
     A0.sort_indices()
     h_colptr, h_rows, h_vals = pin(A0.indptr.astype(np.int64)), pin(A0.indices.astype(np.int32)), pin(A0.data)
     h_labels = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -270,6 +315,8 @@ def run_ours(args):
     launches = ctx.launches - launches0
     st1 = eng.stats()
 
+    import hashlib
+    labels_sha = hashlib.sha256(h_labels.numpy().tobytes()).hexdigest()
     t_dev, t_e2e = float(np.sum(dev_s)), float(np.sum(e2e_s))
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
@@ -277,9 +324,11 @@ def run_ours(args):
         t_dev, t_e2e = float(tt[0]), float(tt[1])
     if rank != 0:
         if world > 1:
+            dist.barrier()  # rank 0 runs the single-GPU extras below
             dist.destroy_process_group()
         return
 
+    extras = {} if args.no_extras else _extras(args, ctx, lib_stream, X, M, arch, A0, A0_raw, world, eng, rss, labels_sha)
     value = n * args.steps / t_dev      # whole job: one n-cell fit per step, however many GPUs share it
     e2e = n * args.steps / t_e2e
     # roofline of the dominant kernel: gradient evaluation of _updateB (k_row_max + k_updateB_eval x2 per FW step)
@@ -299,7 +348,7 @@ def run_ours(args):
                 "bytes_definition": "12 B x nnz(t2) candidate (cell, t2) pairs + 12 B x nnz(K B) row entries + 16 B x n "
                                     "row maxima, each moved once per Frank-Wolfe step (rank 0's shard when N > 1)",
                 "traffic_note": "ncu dram bytes of the two largest kernels of the group are in profiles/*.summary.txt"}
-    cpu_n = 2500
+    cpu_n = 4000
     cpu_dt, cpu_iters, cpu_k = cpu_fit_sample(cpu_n)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -308,6 +357,7 @@ def run_ours(args):
            "config": {"workload": workload_name(n, args.pcs), "cells_per_gpu": n // world if world > 1 else n, "outer_iterations": n_iter,
                       "converged": bool(conv), "rss_first_last": [rss[0], rss[-1]],
                       "fit_seconds": t_dev / args.steps, "construct_kernel_matrix_s": t_build,
+                      "labels_sha256": labels_sha,
                       "l2_policy": "inputs (>= 1 GB of lists per step) exceed the 126 MB L2; no explicit flush",
                       "sharding": ("single GPU" if world == 1 else
                                    f"cells row-sharded over {world} GPUs; per outer iteration one all-gather of the "
@@ -318,9 +368,153 @@ def run_ours(args):
                             "sample": f"full fit() ({cpu_iters} outer iterations) of the oracle restatement of "
                                       f"cpu.SEACellsCPU on a {cpu_n}-cell x 50-PC sample (k={cpu_k}); scipy sparse, "
                                       f"single thread; {os.cpu_count()} host cores available"}}
+    out.update(extras)
     _emit(out)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+
+def _extras(args, ctx, lib_stream, X, M, arch, A0, A0_raw, world, eng, rss, labels_sha):
+    """Single-GPU measurements that ride along on rank 0 after the timed region (none of them enters `value`):
+    parity of the sharded run against an unsharded one, the CSR SpMM roofline probe, the same-config (config 1) pair,
+    and the fit through the reference-facing class (`e2e_api`)."""
+    import hashlib
+
+    import torch
+    from seacells_b200 import FitEngine, SEACells, _lib, build_kernel
+    from seacells_b200.synth import MiniAnnData, synth_archetypes, synth_assignments, synth_embedding
+    lib, ptr = ctx.lib, _lib.ptr
+    n, k = X.shape[0], len(arch)
+    out = {}
+
+    def timed(fn, reps=1):
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(lib_stream)
+            fn()
+            e1.record(lib_stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) / 1e3)
+        return ts
+
+    eng.close()  # the timed engine's 85 GB of device state is no longer needed
+    torch.cuda.empty_cache()
+    # ---- N > 1: the sharded fit must reproduce the single-GPU fit (labels and RSS trajectory to the last bit)
+    if world > 1:
+        e1 = FitEngine(n, k, 50, ctx)
+        e1.set_kernel(M)
+        e1.set_archetypes(arch)
+        e1.set_A(A0)
+        rss1, *_ = e1.run(max_iter=100, min_iter=10, eps=1e-3)
+        sha1 = hashlib.sha256(e1.hard_assignments().astype(np.int32).tobytes()).hexdigest()
+        e1.close()
+        out["parity_vs_1gpu"] = {"labels_identical": sha1 == labels_sha, "rss_identical": list(rss1) == list(rss),
+                                 "labels_sha256_1gpu": sha1, "rss_last_1gpu": rss1[-1], "rss_last": rss[-1]}
+        if sha1 != labels_sha:
+            raise SystemExit(f"bench.py: {world}-GPU hard assignments differ from the 1-GPU fit ({labels_sha} vs {sha1})")
+
+    # ---- CSR SpMM (BASELINE metric "SpMM HBM GB/s vs peak"; cpu_dense.py:353,389 / gpu.py:429,477) at config-2 shape:
+    #      Y[r x c] = M[r x r] X[r x c], r = 100k cells, c = 1333, operands resident in HBM
+    try:
+        r_, c_ = min(100_000, n), min(100_000, n) // 75
+        km2 = build_kernel(X[:r_], 15, "union", ctx)
+        M2, *_ = km2.export(want_knn=False)
+        km2.close()
+        dev = torch.device("cuda", ctx.device)
+        ip = torch.from_numpy(M2.indptr.astype(np.int32)).to(dev)
+        ix = torch.from_numpy(M2.indices.astype(np.int32)).to(dev)
+        dv = torch.from_numpy(M2.data).to(dev)
+        Xd = torch.rand((r_, c_), dtype=torch.float64, device=dev)
+        Yd = torch.empty((r_, c_), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        call = lambda: ctx.check(lib.sc_spmm_csr_f64(ctx.h, r_, r_, c_, ptr(ip), ptr(ix), ptr(dv), ptr(Xd), ptr(Yd)), "spmm")
+        timed(call, 3)
+        ts = timed(call, 10)
+        alg = 12.0 * M2.nnz + 4.0 * (r_ + 1) + 16.0 * c_ * r_
+        peak, src = _peaks()
+        ms = float(np.median(ts)) * 1e3
+        out["spmm"] = {"kernel": "k_spmm_csr_panel (sc_spmm_csr_f64)", "shape": {"r": r_, "m": r_, "c": c_, "nnz": int(M2.nnz)},
+                       "ms": ms, "algorithmic_bytes": alg, "achieved": alg / ms / 1e6, "unit": "GB/s", "peak": peak,
+                       "frac": alg / ms / 1e6 / peak, "peak_source": src, "traffic": _spmm_traffic(),
+                       "bytes_definition": "12 nnz + 4 (r+1) + 8 c m + 8 c r (SURVEY.md 8d): every operand once; the "
+                                           "nnz/r = 24 re-reads of each X row through L2 are not counted"}
+        del Xd, Yd, ip, ix, dv
+        torch.cuda.empty_cache()
+    except Exception as e:  # the probe must never take the headline down
+        out["spmm"] = {"error": repr(e)}
+
+    # ---- same-config pair, GPU side (BASELINE config 1: 10k cells x 50 PCs, k = 133, full fit); the CPU side is the
+    #      `same_config` object of `bench.py --impl reference`
+    if not args.no_same_config:
+        X1 = synth_embedding(C1_CELLS, 50, 0)
+        km1 = build_kernel(X1, 15, "union", ctx)
+        a1, A01 = synth_archetypes(C1_CELLS, C1_K), synth_assignments(C1_CELLS, C1_K)
+        from sklearn.preprocessing import normalize
+        A01n = normalize(A01, axis=0, norm="l1")
+        e1 = FitEngine(C1_CELLS, C1_K, 50, ctx)
+        e1.set_kernel(km1)
+        res = {}
+
+        def fit1():
+            e1.set_archetypes(a1)
+            e1.set_A(A01n)
+            res["r"] = e1.run(max_iter=100, min_iter=10, eps=1e-3)
+
+        timed(fit1, 1)
+        ts = timed(fit1, 3)
+        ad1 = MiniAnnData(X1)
+        m1 = SEACells(ad1, "X_pca", C1_K, verbose=False, use_sparse=True)
+        m1.construct_kernel_matrix()
+        t0 = time.perf_counter()
+        try:
+            m1.fit(max_iter=100, min_iter=10, initial_archetypes=a1, initial_assignments=A01)
+        except RuntimeWarning:
+            pass
+        m1.get_hard_assignments()
+        t_api = time.perf_counter() - t0
+        out["same_config"] = {"config": f"config 1: synthetic {C1_CELLS} cells x 50 PCs, n_SEACells={C1_K}, full fit() "
+                                        f"(initialize + {res['r'][1]} outer iterations)",
+                              "gpu_fit_s": float(np.median(ts)), "gpu_cells_per_s": C1_CELLS / float(np.median(ts)),
+                              "gpu_api_fit_s": t_api, "rss_last": res["r"][0][-1],
+                              "cpu_side": "`same_config.cpu_fit_s` of the `--impl reference` line of the same run"}
+        e1.close()
+        km1.close()
+
+    # ---- the headline configuration through the reference-facing class: SEACells(...).fit() + get_hard_assignments()
+    if world == 1:
+        try:
+            ad = MiniAnnData(X)
+            model = SEACells(ad, "X_pca", k, verbose=False, use_sparse=True)
+            model.add_precomputed_kernel_matrix(M)  # fit() excludes construct_kernel_matrix, as in the reference
+            t0 = time.perf_counter()
+            try:
+                model.fit(max_iter=100, min_iter=10, initial_archetypes=arch, initial_assignments=A0_raw)
+            except RuntimeWarning:
+                pass
+            lab = model.get_hard_assignments()
+            t_api = time.perf_counter() - t0
+            lab_i = np.array([int(x[8:]) for x in lab["SEACell"].values], dtype=np.int32)
+            out["e2e_api"] = {"value": n / t_api, "unit": UNIT, "seconds": t_api,
+                              "call": "seacells_b200.SEACells(ad, 'X_pca', k, use_sparse=True).fit(initial_archetypes=, "
+                                      "initial_assignments=) + get_hard_assignments(): host scipy/numpy inputs, pandas "
+                                      "labels out (includes A0 normalisation, CSR->slot conversion, 1M label strings)",
+                              "labels_identical_to_engine_run": hashlib.sha256(lab_i.tobytes()).hexdigest() == labels_sha}
+        except Exception as e:
+            out["e2e_api"] = {"error": repr(e)}
+    return out
+
+
+def _spmm_traffic():
+    p = os.path.join(ROOT, "profiles", "r2_spmm_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
 
 
 def _emit(obj):
@@ -344,6 +538,8 @@ def main():
     ap.add_argument("--cells", type=int, default=1_000_000)
     ap.add_argument("--pcs", type=int, default=50, help="embedding dimensions (30 for the scATAC-like config 3)")
     ap.add_argument("--kind", default="rna", choices=["rna", "atac"], help="noise spectrum of the synthetic embedding")
+    ap.add_argument("--no-same-config", action="store_true", help="skip the config-1 (10k cells) same-config pair")
+    ap.add_argument("--no-extras", action="store_true", help="skip the spmm / e2e_api / same_config / parity extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

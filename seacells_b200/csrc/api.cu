@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/seacells_b200.h
+#include <cstdlib>
 #include <new>
 
 #include "../../include/seacells_b200.h"
@@ -77,6 +78,53 @@ k_spmm_csr_dense(int r, int c, const int* __restrict__ indptr, const int* __rest
       if (cc < c) yr[cc] = acc[u][0];
       if (cc + 1 < c) yr[cc + 1] = acc[u][1];
     }
+  }
+}
+
+// ---- panel-ordered variant.  With ~24 stored entries per row every row of X is gathered ~24 times; X (8 c m bytes, 1 GB
+// at the config-2 shape) does not fit the 126 MB L2, so in the row-major kernel above most of those gathers go to HBM.
+// Here the CTAs are ordered panel-major: all rows for columns [0, W), then [W, 2W), ...  One panel of X (8 W m bytes:
+// 51 MB for W = 64 at m = 100k) plus the CSR arrays stay L2-resident while the panel is processed, so HBM sees every
+// operand about once (the algorithmic bytes of SURVEY.md 8d) and the re-reads are served by L2.
+// One warp per (row, panel); lane l owns columns c0 + l + 32 j: every load instruction of a warp reads 256 contiguous
+// bytes of one X row (c is odd at the config shapes - 133, 1333, 13333 - so rows are only 8-byte aligned and a double2
+// mapping would split sectors).
+template <int W>
+__global__ void __launch_bounds__(256)
+k_spmm_csr_panel(int r, int c, const int* __restrict__ indptr, const int* __restrict__ indices,
+                 const double* __restrict__ data, const double* __restrict__ X, double* __restrict__ Y, int row_blocks) {
+  constexpr int ROWS_PER_CTA = 64, U = W / 32;
+  const int panel = blockIdx.x / row_blocks, rb = blockIdx.x - panel * row_blocks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = panel * W + lane;
+  const int row_end = min(r, (rb + 1) * ROWS_PER_CTA);
+  for (int row = rb * ROWS_PER_CTA + warp; row < row_end; row += 8) {
+    const int s0 = indptr[row], s1 = indptr[row + 1];
+    double acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    for (int base = s0; base < s1; base += 32) {
+      int q = 0;
+      double m = 0.0;
+      if (base + lane < s1) {
+        q = indices[base + lane];
+        m = data[base + lane];
+      }
+      const int cnt = min(32, s1 - base);
+#pragma unroll 8
+      for (int e = 0; e < cnt; ++e) {
+        const int qq = __shfl_sync(0xffffffffu, q, e);
+        const double mm = __shfl_sync(0xffffffffu, m, e);
+        const double* xr = X + (size_t)qq * c + c0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (c0 + u * 32 < c) acc[u] = fma(mm, __ldg(xr + u * 32), acc[u]);
+      }
+    }
+    double* yr = Y + (size_t)row * c + c0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c0 + u * 32 < c) yr[u * 32] = acc[u];
   }
 }
 
@@ -321,9 +369,20 @@ int sc_spmm_csr_f64(sc_ctx* ctx, int r, int m, int c, const int32_t* indptr, con
     SC_TRY(sy.ensure(ctx, (size_t)r * c));
     dy = sy.p;
   }
-  const int chunks = (c + 255) / 256;
-  const long long warps = (long long)r * chunks;
-  SC_LAUNCH(ctx, k_spmm_csr_dense, (unsigned)((warps * 32 + 255) / 256), 256, 0, r, c, dp, dc, dv, dx, dy, chunks);
+  // SC_SPMM_PANEL = 0: row-major kernel; 64 / 128: panel width of the L2-blocked kernel (default 64)
+  int panel_w = 64;
+  if (const char* e = std::getenv("SC_SPMM_PANEL")) panel_w = atoi(e);
+  if (panel_w == 64 || panel_w == 128) {
+    const int row_blocks = (r + 63) / 64;
+    const int panels = (c + panel_w - 1) / panel_w;
+    const unsigned grid = (unsigned)((long long)row_blocks * panels);
+    if (panel_w == 64) SC_LAUNCH(ctx, k_spmm_csr_panel<64>, grid, 256, 0, r, c, dp, dc, dv, dx, dy, row_blocks);
+    else SC_LAUNCH(ctx, k_spmm_csr_panel<128>, grid, 256, 0, r, c, dp, dc, dv, dx, dy, row_blocks);
+  } else {
+    const int chunks = (c + 255) / 256;
+    const long long warps = (long long)r * chunks;
+    SC_LAUNCH(ctx, k_spmm_csr_dense, (unsigned)((warps * 32 + 255) / 256), 256, 0, r, c, dp, dc, dv, dx, dy, chunks);
+  }
   if (!y_dev) SC_CUDA(ctx, sc_copy(Y, dy, sizeof(double) * (size_t)r * c, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SC_OK;

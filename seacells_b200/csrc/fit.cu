@@ -665,60 +665,85 @@ __global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restric
 // incremental = 0: HH[cell, :] = (rows of KB) x T1H, evaluated in full.
 // incremental = 1: KB holds only the step's delta rows K E (see k_kb_merge) and HH the product for the previous B:
 //                  HH <- c_old HH + c_new (delta rows x T1H)  - the same identity as for K B itself, 8x fewer entries.
-__global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end, int nh_pad,
-                                                     const int* __restrict__ perm, RowLists KB,
-                                                     const double* __restrict__ T1H, const double* __restrict__ T2H,
-                                                     double* __restrict__ HH, int incremental, double c_old, double c_new,
-                                                     double* __restrict__ out) {
+// Four cells per warp iteration: their HH / t2 rows and list headers are requested before any of them is consumed, so a
+// warp keeps ~20 independent loads in flight instead of walking one cell through four dependent round trips (the first
+// version ran at 37 % warps active and 1.4 TB/s; it was latency bound, not bandwidth bound).  Lane l owns hubs l, l + 32,
+// ...; R = nh_pad / 32.  Per (cell, hub) the arithmetic and its order are unchanged.
+template <int R, int HUB_UNROLL>
+__global__ void __launch_bounds__(256, 2) k_updateB_hub(int row_begin, int row_end, int nh_pad,
+                                                        const int* __restrict__ perm, RowLists KB,
+                                                        const double* __restrict__ T1H, const double* __restrict__ T2H,
+                                                        double* __restrict__ HH, int incremental, double c_old,
+                                                        double c_new, double* __restrict__ out) {
   __shared__ double s_v[8][2][HUB_MAX];
   __shared__ int s_i[8][2][HUB_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = nh_pad >> 5;
-  double cv[4], nv[4];
-  int ci[4], ni[4];
+  double cv[R], nv[R];
+  int ci[R], ni[R];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < R; ++r) {
     cv[r] = nv[r] = FW_INF;
     ci[r] = ni[r] = 0x7fffffff;
   }
   const int c0 = row_begin + blockIdx.x * HUB_CELLS_PER_CTA;
   const int c1 = min(row_end, c0 + HUB_CELLS_PER_CTA);
-  for (int ii = c0 + warp; ii < c1; ii += 8) {
-    const int i = perm[ii - row_begin];  // locality order; ties below are resolved on the cell index explicitly
-    const long long p = KB.ptr[i];
-    const int L = KB.len[i];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int x0 = 0; x0 < L; x0 += 32) {
-      int key = 0;
-      double val = 0.0;
-      if (x0 + lane < L) {
-        key = KB.key[p + x0 + lane];
-        val = KB.val[p + x0 + lane];
-      }
-      const int cnt = min(32, L - x0);
-#pragma unroll 4
-      for (int e = 0; e < cnt; ++e) {
-        const int l = __shfl_sync(0xffffffffu, key, e);
-        const double v = __shfl_sync(0xffffffffu, val, e);
-        const double* __restrict__ trow = T1H + (size_t)l * nh_pad + lane;
+  for (int ii = c0 + warp * HUB_UNROLL; ii < c1; ii += 8 * HUB_UNROLL) {
+    int cell[HUB_UNROLL], L[HUB_UNROLL];
+    long long p[HUB_UNROLL];
+    double hh[HUB_UNROLL][R], t2[HUB_UNROLL][R], acc[HUB_UNROLL][R];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          if (r < R) acc[r] = fma(v, __ldg(trow + r * 32), acc[r]);
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      cell[u] = (ii + u < c1) ? perm[ii + u - row_begin] : -1;  // locality order; ties are resolved on the cell index
+    }
+#pragma unroll
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      p[u] = 0;
+      L[u] = 0;
+      if (cell[u] >= 0) {
+        p[u] = KB.ptr[cell[u]];
+        L[u] = KB.len[cell[u]];
+        const size_t ro = (size_t)(cell[u] - row_begin) * nh_pad + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          hh[u][r] = incremental ? HH[ro + r * 32] : 0.0;
+          t2[u][r] = T2H[ro + r * 32];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[u][r] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      for (int x0 = 0; x0 < L[u]; x0 += 32) {
+        int key = 0;
+        double val = 0.0;
+        if (x0 + lane < L[u]) {
+          key = KB.key[p[u] + x0 + lane];
+          val = KB.val[p[u] + x0 + lane];
+        }
+        const int cnt = min(32, L[u] - x0);
+#pragma unroll 4
+        for (int e = 0; e < cnt; ++e) {
+          const int l = __shfl_sync(0xffffffffu, key, e);
+          const double v = __shfl_sync(0xffffffffu, val, e);
+          const double* __restrict__ trow = T1H + (size_t)l * nh_pad + lane;
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[u][r] = fma(v, __ldg(trow + r * 32), acc[u][r]);
+        }
       }
     }
-    double* __restrict__ hrow = HH + (size_t)(i - row_begin) * nh_pad + lane;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if (r < R) {
-        if (incremental) acc[r] = __dadd_rn(__dmul_rn(c_old, hrow[r * 32]), __dmul_rn(c_new, acc[r]));
-        hrow[r * 32] = acc[r];
-      }
-    const double* __restrict__ t2row = T2H + (size_t)(i - row_begin) * nh_pad + lane;
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      if (cell[u] < 0) continue;
+      const int i = cell[u];
+      double* __restrict__ hrow = HH + (size_t)(i - row_begin) * nh_pad + lane;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if (r < R) {
-        const double t2v = t2row[r * 32];
-        const double G = 2.0 * (acc[r] - t2v);
+      for (int r = 0; r < R; ++r) {
+        double a = acc[u][r];
+        if (incremental) a = __dadd_rn(__dmul_rn(c_old, hh[u][r]), __dmul_rn(c_new, a));
+        hrow[r * 32] = a;
+        const double t2v = t2[u][r];
+        const double G = 2.0 * (a - t2v);
         if (t2v > 0.0) {
           if (G < cv[r] || (G == cv[r] && i < ci[r])) {
             cv[r] = G;
@@ -729,15 +754,15 @@ __global__ void __launch_bounds__(256) k_updateB_hub(int row_begin, int row_end,
           ni[r] = i;
         }
       }
+    }
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-    if (r < R) {
-      s_v[warp][0][r * 32 + lane] = cv[r];
-      s_i[warp][0][r * 32 + lane] = ci[r];
-      s_v[warp][1][r * 32 + lane] = nv[r];
-      s_i[warp][1][r * 32 + lane] = ni[r];
-    }
+  for (int r = 0; r < R; ++r) {
+    s_v[warp][0][r * 32 + lane] = cv[r];
+    s_i[warp][0][r * 32 + lane] = ci[r];
+    s_v[warp][1][r * 32 + lane] = nv[r];
+    s_i[warp][1][r * 32 + lane] = ni[r];
+  }
   __syncthreads();
   for (int t = threadIdx.x; t < 2 * nh_pad; t += 256) {
     const int kind = t / nh_pad, slot = t - kind * nh_pad;
@@ -1926,8 +1951,17 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     // steps 0 and 1 evaluate the product in full (K B from the previous B, then K E_0); later steps advance it
     const bool inc = !fresh_kb && t >= 2;
     const double gamma = inc ? 2.0 / ((double)(t - 1) + 2.0) : 0.0;
-    SC_LAUNCH(ctx, k_updateB_hub, nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, inc ? DKB.view() : KB.view(),
-              T1H.p, T2H.p, HH.p, inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p);
+    const RowLists hub_rows = inc ? DKB.view() : KB.view();
+#define SC_HUB_LAUNCH(RR)                                                                                              \
+  SC_LAUNCH(ctx, (k_updateB_hub<RR, (RR <= 2 ? 4 : 2)>), nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, hub_rows, T1H.p, T2H.p, HH.p, \
+            inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p)
+    switch (n_hub_pad / 32) {
+      case 1: SC_HUB_LAUNCH(1); break;
+      case 2: SC_HUB_LAUNCH(2); break;
+      case 3: SC_HUB_LAUNCH(3); break;
+      default: SC_HUB_LAUNCH(4); break;
+    }
+#undef SC_HUB_LAUNCH
     SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));

@@ -237,17 +237,18 @@ def run_ours(args):
     ctx = _lib.default_context(local)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
-    # N > 1: ONE n-cell fit, cells row-sharded over the ranks (strong scaling; seacells_b200/parallel.py).
-    # Every rank holds the same embedding; the kNN queries are sharded too, the kernel matrix is replicated.
-    from seacells_b200.parallel import ShardedFit, sharded_knn
+    # N > 1: ONE n-cell fit, cells row-sharded over the ranks (strong scaling).  The context joins the job (the library's
+    # own NCCL communicator, bootstrapped through torch.distributed); from then on sc_kernel_build / sc_fit_run exchange
+    # what the other ranks need inside the library.  Every rank holds the same embedding.
+    from seacells_b200.parallel import init_nccl
+    init_nccl(ctx)
     n = args.cells
     k = n // 75
     X = synth_embedding(n, args.pcs, seed=0, kind=args.kind)
     build_kernel(X[:4096], 15, "union", ctx).close()  # untimed: CUDA context, module load, first allocations
     ctx.sync()
     t0 = time.perf_counter()
-    knn_graph = sharded_knn(X, 15, ctx) if world > 1 else None
-    km = build_kernel(X, 15, "union", ctx, knn_graph=knn_graph)
+    km = build_kernel(X, 15, "union", ctx)
     ctx.sync()
     t_build = time.perf_counter() - t0
     import ctypes as C
@@ -269,7 +270,6 @@ def run_ours(args):
     d2h = 4 * n + 8 * 102
 
     eng = FitEngine(n, k, 50, ctx)
-    sharded = ShardedFit(eng) if world > 1 else None
     lib = ctx.lib
     ptr = _lib.ptr
 
@@ -280,10 +280,7 @@ def run_ours(args):
         eng.set_archetypes(arch)
         ctx.check(lib.sc_fit_set_A_csc(eng.h, ptr(h_colptr), ptr(h_rows), ptr(h_vals)), "set_A")
         ev[1].record(lib_stream)
-        if sharded is not None:
-            rss, n_iter, conv, thr = sharded.run(max_iter=100, min_iter=10, eps=1e-3)
-        else:
-            rss, n_iter, conv, thr = eng.run(max_iter=100, min_iter=10, eps=1e-3)
+        rss, n_iter, conv, thr = eng.run(max_iter=100, min_iter=10, eps=1e-3)
         ev[2].record(lib_stream)
         ctx.check(lib.sc_fit_hard_assignments(eng.h, ptr(h_labels)), "labels")
         ev[3].record(lib_stream)
@@ -360,8 +357,9 @@ def run_ours(args):
                       "labels_sha256": labels_sha,
                       "l2_policy": "inputs (>= 1 GB of lists per step) exceed the 126 MB L2; no explicit flush",
                       "sharding": ("single GPU" if world == 1 else
-                                   f"cells row-sharded over {world} GPUs; per outer iteration one all-gather of the "
-                                   "compressed A and 50 all-gathers of k x 4 fp64 argmin partials (NCCL)")},
+                                   f"cells row-sharded over {world} GPUs; in-library NCCL all-gathers: per outer "
+                                   "iteration the compressed A (x1), per-cell RSS terms (x1), candidate counts (x1) and "
+                                   "50 x k x 4 fp64 argmin partials")},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "knn": knn_info,
            "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": 1, "kind": "port",
@@ -404,17 +402,20 @@ def _extras(args, ctx, lib_stream, X, M, arch, A0, A0_raw, world, eng, rss, labe
     torch.cuda.empty_cache()
     # ---- N > 1: the sharded fit must reproduce the single-GPU fit (labels and RSS trajectory to the last bit)
     if world > 1:
-        e1 = FitEngine(n, k, 50, ctx)
+        solo = _lib.Context(ctx.device)   # a context that is not part of the job: plain single-GPU fit
+        e1 = FitEngine(n, k, 50, solo)
         e1.set_kernel(M)
         e1.set_archetypes(arch)
         e1.set_A(A0)
         rss1, *_ = e1.run(max_iter=100, min_iter=10, eps=1e-3)
         sha1 = hashlib.sha256(e1.hard_assignments().astype(np.int32).tobytes()).hexdigest()
         e1.close()
+        solo.close()
         out["parity_vs_1gpu"] = {"labels_identical": sha1 == labels_sha, "rss_identical": list(rss1) == list(rss),
                                  "labels_sha256_1gpu": sha1, "rss_last_1gpu": rss1[-1], "rss_last": rss[-1]}
         if sha1 != labels_sha:
             raise SystemExit(f"bench.py: {world}-GPU hard assignments differ from the 1-GPU fit ({labels_sha} vs {sha1})")
+        return out  # the remaining probes are single-GPU measurements: they ride on the N = 1 line only
 
     # ---- CSR SpMM (BASELINE metric "SpMM HBM GB/s vs peak"; cpu_dense.py:353,389 / gpu.py:429,477) at config-2 shape:
     #      Y[r x c] = M[r x r] X[r x c], r = 100k cells, c = 1333, operands resident in HBM

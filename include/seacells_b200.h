@@ -41,6 +41,29 @@ int sc_sync(sc_ctx* ctx);
 void* sc_stream(sc_ctx* ctx); /* cudaStream_t the library launches on (for CUDA-event timing) */
 const char* sc_version(void);
 
+/* ---- row-sharded jobs: one context per rank, one rank per GPU ------------------------------
+ * The reference has no distributed code; this is the engine's own scale-out.  A context that belongs to a job of `world`
+ * ranks owns the cells [rank * slab, (rank + 1) * slab), slab = ceil(n / world): sc_kernel_build searches the neighbours
+ * of its slab only, sc_fit_update_A fills its columns of A, sc_fit_update_B evaluates its rows of the gradient, and the
+ * library exchanges what the other ranks need on its own stream with ONE collective, an in-place all-gather of equal
+ * slabs (compressed A, per-cell RSS terms, per-archetype {candidate min G, cell, non-candidate G, cell} argmin partials,
+ * kNN rows, candidate counts).  No floating-point value is reduced across ranks, so results are bitwise identical to a
+ * single-GPU run.  Every rank must make the same calls in the same order with the same M, archetypes and A0.
+ *   sc_nccl_unique_id + sc_ctx_init_nccl   one process per GPU: rank 0 creates the 128-byte id, the host broadcasts it
+ *                                          (torch.distributed, MPI, a file ...), every rank joins; libnccl.so.2 is
+ *                                          resolved with dlopen (sc_nccl_load_library gives an explicit path)
+ *   sc_local_group_new + sc_ctx_attach_local   ranks are threads of one process (one context each, on one or on several
+ *                                          GPUs); slabs move with peer copies between thread barriers */
+int sc_nccl_load_library(const char* path);
+int sc_nccl_unique_id(void* out128);
+int sc_ctx_init_nccl(sc_ctx* ctx, int rank, int world, const void* id128);
+int sc_local_group_new(int world, void** group_out);
+void sc_local_group_free(void* group);
+void sc_local_group_abort(void* group); /* a rank failed: peers blocked in an exchange return SC_ERR_NCCL */
+int sc_ctx_attach_local(sc_ctx* ctx, void* group, int rank);
+int sc_ctx_rank(sc_ctx* ctx);
+int sc_ctx_world(sc_ctx* ctx);
+
 /* ---- hot path 1: kernel construction  (build_graph.SEACellGraph.rbf, build_graph.py:113-189) -------------------- */
 
 /* Replaces scanpy.pp.neighbors(ad, use_rep, n_neighbors, knn=True) at build_graph.py:125 with an exact brute-force
@@ -104,7 +127,8 @@ int sc_greedy_centers(sc_ctx* ctx, int n, const int32_t* indptr, const int32_t* 
 int sc_fit_create(sc_ctx* ctx, int n_cells, int n_archetypes, int max_FW_iter, sc_fit** out);
 void sc_fit_destroy(sc_fit* fit);
 
-/* add_precomputed_kernel_matrix (cpu.py:115-128): M as CSR with sorted columns; K = M M^T is applied, never formed */
+/* add_precomputed_kernel_matrix (cpu.py:115-128): M as CSR with sorted columns, symmetric and non-negative (checked);
+ * K = M M^T is formed on the device here, as the reference does at cpu.py:127,157 */
 int sc_fit_set_kernel(sc_fit* fit, const int32_t* indptr, const int32_t* indices, const double* data, long long nnz);
 int sc_fit_set_kernel_from(sc_fit* fit, sc_kernel* km); /* device-to-device hand-off from sc_kernel_build */
 
@@ -121,23 +145,8 @@ int sc_fit_set_B_slots(sc_fit* fit, const int32_t* idx, const double* val, const
 int sc_fit_update_A(sc_fit* fit, double l2_penalty, int32_t* trace);
 /* _updateB (cpu.py:461-498).  trace: NULL or host int32 [max_FW_iter x k]. */
 int sc_fit_update_B(sc_fit* fit, int32_t* trace);
-/* ---- multi-GPU (one process per GPU; cells sharded by contiguous slabs) ---------------------------
- * The library never communicates: the host (torch.distributed / NCCL) moves two things between these calls.
- *   sc_fit_set_shard      this rank owns cells [row_begin,row_end): _updateA fills only those columns of A, and the
- *                         candidate lists / K*B rows of _updateB are built for those cells only.
- *   sc_fit_A_slots_device device pointers of the current compressed A (idx int32 [rows,S], val fp64 [rows,S],
- *                         cnt int32 [rows], rows = n+64 so equal slabs can be all-gathered in place) - all-gather them
- *                         after every sc_fit_update_A.
- *   _updateB in phases    begin (Gram, t2, candidates); then per Frank-Wolfe step t: eval writes this rank's
- *                         per-archetype partial {cand min G, cell, non-candidate G, cell} (k x 4 fp64, device) -> the
- *                         host all-gathers the partials -> step merges them and updates the replicated B; end.
- *   sc_fit_update_B is exactly begin + T x (eval, step with n_ranks = 1) + end. */
-int sc_fit_set_shard(sc_fit* fit, int row_begin, int row_end);
-int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long long* rows_allocated);
-int sc_fit_update_B_begin(sc_fit* fit);
-int sc_fit_update_B_eval(sc_fit* fit, int t, double* partial_dev /* [k*4] device */);
-int sc_fit_update_B_step(sc_fit* fit, int t, const double* gathered_dev /* [n_ranks][k*4] device */, int n_ranks);
-int sc_fit_update_B_end(sc_fit* fit);
+/* cells [row_begin, row_end) owned by this handle's rank (the whole range on one GPU) */
+int sc_fit_shard(sc_fit* fit, int* row_begin, int* row_end);
 
 /* compute_RSS (cpu.py:520-536): || M - (M B) A ||_F via the trace identity, no n x n product */
 int sc_fit_rss(sc_fit* fit, double* rss_out);
@@ -164,12 +173,16 @@ int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
  * [2] archetypes in the cell-major hub block of the last _updateB, [3] rows (cumulative over the life of the handle)
  * that needed the dense-accumulator kernel of the sparse product, [4] (cell, archetype) gradients evaluated exactly in the last _updateB (all
  * Frank-Wolfe steps together; the rest of nnz(t2) x max_FW_iter was pruned by the lower bounds), [5] Frank-Wolfe
- * steps of _updateB timed so far and [6] their summed CUDA-event time in ns for the gradient kernel (row max + both
- * rounds of k_updateB_eval), [7] nnz of the last K*B row lists.  out: 8 values. */
-int sc_fit_stats(sc_fit* fit, long long* out8);
+ * steps of _updateB timed so far and [6] their summed CUDA-event time in ns for the gradient launch group (row maxima when
+ * not produced by the merge, both rounds of k_updateB_eval, k_updateB_hub and its reduction, the locality permutation at
+ * step 0), [7] nnz of the last K*B row lists, [8] steps timed and [9] summed CUDA-event ns of k_updateB_hub alone,
+ * [10] its algorithmic bytes per launch (24 B x cells x padded hubs + 12 B x delta entries).  out: 16 values. */
+int sc_fit_stats(sc_fit* fit, long long* out16);
 /* with SC_PROFILE=1 in the environment: accumulated wall seconds per stage (synchronising; development aid).
  * [0] B-by-cell [1] M*B [2] M*(M*B) [3] t1=B^T K B [4] _updateA shared-memory path [5] _updateA generic path
- * [6] A A^T [7] K A^T rows [8] candidates by archetype [9] _updateB gradient+argmin+step [10] RSS */
+ * [6] A A^T [7] K A^T rows [8] candidates by archetype [9] _updateB gradient+argmin+step [10] RSS
+ * ([0] push sources of K B, [1] K E_t of the Frank-Wolfe steps, [2] K B and the per-step merges since the products use the
+ * explicit K) */
 int sc_fit_profile(sc_fit* fit, double* out16);
 
 #ifdef __cplusplus

@@ -32,6 +32,15 @@ SIGNATURES = {
     "sc_sync": (_i, [_vp]),
     "sc_stream": (_vp, [_vp]),
     "sc_version": (C.c_char_p, []),
+    "sc_nccl_load_library": (_i, [C.c_char_p]),
+    "sc_nccl_unique_id": (_i, [_vp]),
+    "sc_ctx_init_nccl": (_i, [_vp, _i, _i, _vp]),
+    "sc_local_group_new": (_i, [_i, _pp]),
+    "sc_local_group_free": (None, [_vp]),
+    "sc_local_group_abort": (None, [_vp]),
+    "sc_ctx_attach_local": (_i, [_vp, _vp, _i]),
+    "sc_ctx_rank": (_i, [_vp]),
+    "sc_ctx_world": (_i, [_vp]),
     "sc_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sc_knn_tc_probe": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sc_knn_tc_error_factor": (_d, [_i]),
@@ -53,12 +62,7 @@ SIGNATURES = {
     "sc_fit_update_A": (_i, [_vp, _d, _vp]),
     "sc_fit_update_B": (_i, [_vp, _vp]),
     "sc_fit_rss": (_i, [_vp, C.POINTER(_d)]),
-    "sc_fit_set_shard": (_i, [_vp, _i, _i]),
-    "sc_fit_A_slots_device": (_i, [_vp, _pp, _pp, _pp, C.POINTER(_ll)]),
-    "sc_fit_update_B_begin": (_i, [_vp]),
-    "sc_fit_update_B_eval": (_i, [_vp, _i, _vp]),
-    "sc_fit_update_B_step": (_i, [_vp, _i, _vp, _i]),
-    "sc_fit_update_B_end": (_i, [_vp]),
+    "sc_fit_shard": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "sc_fit_run": (_i, [_vp, _i, _i, _d, _d, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp, _i, C.POINTER(_i)]),
     "sc_fit_get_KB": (_i, [_vp, C.POINTER(_ll), _vp, _vp, _vp]),
     "sc_fit_slots": (_i, [_vp]),
@@ -125,6 +129,14 @@ class Context:
         if rc != SC_OK:
             msg = self.lib.sc_last_error(self.h)
             raise SeacellsB200Error(f"{what} failed ({_ERRNAMES.get(rc, rc)}): {msg.decode() if msg else ''}")
+
+    @property
+    def rank(self) -> int:
+        return int(self.lib.sc_ctx_rank(self.h))
+
+    @property
+    def world(self) -> int:
+        return int(self.lib.sc_ctx_world(self.h))
 
     @property
     def launches(self) -> int:

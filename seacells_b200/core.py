@@ -288,14 +288,21 @@ class FitEngine:
         return idx, w
 
     def stats(self):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(16, np.int64)
         self.ctx.check(self.ctx.lib.sc_fit_stats(self.h, ptr(out)), "sc_fit_stats")
         return {"slow_cells_last_update_A": int(out[0]), "t2_nnz_last_update_B": int(out[1]),
                 "hub_archetypes_last_update_B": int(out[2]), "dense_rows_spgemm_total": int(out[3]),
                 "gradients_evaluated_last_update_B": int(out[4]), "updB_steps_timed": int(out[5]),
-                "updB_eval_ns_total": int(out[6]), "kb_nnz_last": int(out[7])}
+                "updB_eval_ns_total": int(out[6]), "kb_nnz_last": int(out[7]), "hub_steps_timed": int(out[8]),
+                "hub_ns_total": int(out[9]), "hub_bytes_per_launch": int(out[10])}
 
-    STAGES = ["brow", "M*B", "M*(M*B)", "t1A", "updA_smem", "updA_generic", "gram", "KAt_rows", "cand_by_arch",
+    def shard(self):
+        """Cells [begin, end) this rank owns (the whole range on one GPU)."""
+        b, e = C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.sc_fit_shard(self.h, C.byref(b), C.byref(e)), "sc_fit_shard")
+        return int(b.value), int(e.value)
+
+    STAGES = ["KB_sources", "KE_step", "KB+merge", "t1A", "updA_smem", "updA_generic", "gram", "KAt_rows", "cand_by_arch",
               "updB_step", "rss"]
 
     def profile(self):

@@ -1,8 +1,10 @@
 // extern "C" surface declared in include/seacells_b200.h
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 
 #include "../../include/seacells_b200.h"
+#include "comm.cuh"
 #include "common.cuh"
 #include "fit.cuh"
 #include "kernel_build.cuh"
@@ -155,10 +157,50 @@ int sc_ctx_create(int device, sc_ctx** out) {
   return SC_OK;
 }
 
+// ---- row-sharded jobs: one context per rank ----------------------------------------------------------
+int sc_nccl_load_library(const char* path) {
+  std::string err;
+  return sc_nccl_load(path, &err);
+}
+int sc_nccl_unique_id(void* out128) {
+  if (!out128) return SC_ERR_ARG;
+  std::string err;
+  return sc_nccl_get_unique_id(out128, &err);
+}
+int sc_ctx_init_nccl(sc_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return SC_ERR_ARG;
+  if (ctx->comm) SC_FAIL(ctx, SC_ERR_STATE, "context already belongs to a sharded job");
+  DeviceGuard dev_guard(ctx->device);
+  std::string err;
+  sc_comm* c = sc_nccl_comm_create(rank, world, id128, &err);
+  if (!c) SC_FAIL(ctx, SC_ERR_NCCL, err);
+  ctx->comm = c;
+  return SC_OK;
+}
+int sc_local_group_new(int world, void** out) {
+  if (!out || world < 1) return SC_ERR_ARG;
+  *out = sc_local_group_create(world);
+  return *out ? SC_OK : SC_ERR_ARG;
+}
+void sc_local_group_free(void* group) { sc_local_group_destroy((sc_comm_group*)group); }
+void sc_local_group_abort(void* group) { sc_local_group_break((sc_comm_group*)group); }
+int sc_ctx_attach_local(sc_ctx* ctx, void* group, int rank) {
+  if (!ctx || !group) return SC_ERR_ARG;
+  if (ctx->comm) SC_FAIL(ctx, SC_ERR_STATE, "context already belongs to a sharded job");
+  sc_comm* c = sc_local_comm_create((sc_comm_group*)group, rank);
+  if (!c) SC_FAIL(ctx, SC_ERR_ARG, "bad rank for this group");
+  ctx->comm = c;
+  return SC_OK;
+}
+int sc_ctx_rank(sc_ctx* ctx) { return ctx ? ctx->rank() : 0; }
+int sc_ctx_world(sc_ctx* ctx) { return ctx ? ctx->world() : 1; }
+
 void sc_ctx_destroy(sc_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard dev_guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  delete ctx->comm;
+  ctx->comm = nullptr;
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -295,8 +337,12 @@ static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, in
   if (!km) SC_FAIL(ctx, SC_ERR_CUDA, "out of host memory");
   const int kk = n_neighbors - 1;
   km->kk = kk;
-  int rc = km->knn_idx.ensure(ctx, (size_t)n * kk + 1);
-  if (rc == SC_OK) rc = km->knn_d2.ensure(ctx, (size_t)n * kk + 1);
+  // a rank of a sharded job searches the neighbours of its own slab of query cells; the slabs are all-gathered on the
+  // device (112 MB at 1M cells) and every rank then assembles the same symmetric matrix (build_graph.py:125-147)
+  const int world = ctx->world();
+  const int slab = (n + world - 1) / world;
+  int rc = km->knn_idx.ensure(ctx, (size_t)slab * world * kk + 1);
+  if (rc == SC_OK) rc = km->knn_d2.ensure(ctx, (size_t)slab * world * kk + 1);
   if (rc == SC_OK) {
     if (idx && d2) {
       if (cudaMemcpyAsync(km->knn_idx.p, idx, sizeof(int) * (size_t)n * kk, cudaMemcpyDefault, ctx->stream) != cudaSuccess ||
@@ -304,8 +350,16 @@ static int kernel_build_impl(sc_ctx* ctx, const void* X, int x_is_f64, int n, in
         ctx->err = "kernel_build: copying the kNN graph failed";
         rc = SC_ERR_CUDA;
       }
-    } else {
+    } else if (world == 1) {
       rc = sc_knn_exact_dev(ctx, Xd, x_is_f64, n, d, n_neighbors, 0, n, km->knn_idx.p, km->knn_d2.p);
+    } else {
+      const int r0 = std::min(n, ctx->rank() * slab), r1 = std::min(n, r0 + slab);
+      if (r1 > r0)
+        rc = sc_knn_exact_dev(ctx, Xd, x_is_f64, n, d, n_neighbors, r0, r1, km->knn_idx.p + (size_t)r0 * kk,
+                              km->knn_d2.p + (size_t)r0 * kk);
+      if (rc == SC_OK) rc = ctx->comm->allgather(km->knn_idx.p, sizeof(int) * (size_t)slab * kk, ctx->stream);
+      if (rc == SC_OK) rc = ctx->comm->allgather(km->knn_d2.p, sizeof(double) * (size_t)slab * kk, ctx->stream);
+      if (rc != SC_OK && ctx->err.empty()) ctx->err = ctx->comm->err;
     }
   }
   if (rc == SC_OK) rc = km->build(ctx, Xd, x_is_f64, n, d, n_neighbors, km->knn_idx.p, km->knn_d2.p, intersection);
@@ -484,44 +538,11 @@ int sc_fit_update_B(sc_fit* fit, int32_t* trace) {
   return with_trace(fit, trace, (size_t)fit->T * fit->k, [](sc_fit* f, int* t, double) { return f->update_B(t); }, 0.0);
 }
 
-int sc_fit_set_shard(sc_fit* fit, int row_begin, int row_end) {
-  if (!fit) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  return fit->set_shard(row_begin, row_end);
-}
-
-int sc_fit_A_slots_device(sc_fit* fit, void** idx, void** val, void** cnt, long long* rows_allocated) {
-  if (!fit || !idx || !val || !cnt) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  if (!fit->have_A || !fit->a_is_slots) SC_FAIL(fit->ctx, SC_ERR_STATE, "fit: A has not been computed");
-  *idx = fit->a_idx[fit->a_cur].p;
-  *val = fit->a_val[fit->a_cur].p;
-  *cnt = fit->a_cnt[fit->a_cur].p;
-  if (rows_allocated) *rows_allocated = (long long)fit->n + 64;
+int sc_fit_shard(sc_fit* fit, int* row_begin, int* row_end) {
+  if (!fit || !row_begin || !row_end) return SC_ERR_ARG;
+  *row_begin = fit->row_begin;
+  *row_end = fit->row_end;
   return SC_OK;
-}
-
-int sc_fit_update_B_begin(sc_fit* fit) {
-  if (!fit) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  return fit->update_B_begin();
-}
-int sc_fit_update_B_eval(sc_fit* fit, int t, double* partial_dev) {
-  if (!fit || !partial_dev) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  if (!sc_is_device_ptr(partial_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_eval: partial buffer must be device memory");
-  return fit->update_B_eval(t, partial_dev);
-}
-int sc_fit_update_B_step(sc_fit* fit, int t, const double* gathered_dev, int n_ranks) {
-  if (!fit || !gathered_dev || n_ranks < 1) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  if (!sc_is_device_ptr(gathered_dev)) SC_FAIL(fit->ctx, SC_ERR_ARG, "update_B_step: gathered buffer must be device memory");
-  return fit->update_B_step(t, gathered_dev, n_ranks, nullptr);
-}
-int sc_fit_update_B_end(sc_fit* fit) {
-  if (!fit) return SC_ERR_ARG;
-  DeviceGuard dev_guard(fit->ctx->device);
-  return fit->update_B_end();
 }
 
 int sc_fit_rss(sc_fit* fit, double* rss_out) {
@@ -581,6 +602,10 @@ int sc_fit_stats(sc_fit* fit, long long* out4) {
   out4[1] = fit->last_t2_nnz;
   out4[2] = fit->last_hub_block;
   out4[3] = fit->sp.total_big_rows;
+  out4[8] = fit->hub_steps;
+  out4[9] = (long long)(fit->hub_ms_total * 1e6);
+  out4[10] = fit->hub_launches_counted ? (long long)(fit->hub_bytes_total / (double)fit->hub_launches_counted) : 0;
+  for (int i = 11; i < 16; ++i) out4[i] = 0;
   return SC_OK;
 }
 int sc_fit_profile(sc_fit* fit, double* out16) {

@@ -24,8 +24,9 @@ struct sc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  int rank = 0, world = 1;
-  void* nccl = nullptr;  // ncclComm_t when world > 1
+  struct sc_comm* comm = nullptr;  // set when this context is one rank of a row-sharded job (comm.cuh); owned by the ctx
+  int rank() const;
+  int world() const;
   // launch counter: every kernel launched by the library goes through SC_LAUNCH and bumps this
   unsigned long long launches = 0;
   int last_knn_fallback = 0;  // queries of the last kNN call that failed the filter certificate (recomputed exactly)
@@ -153,7 +154,7 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 int sc_exclusive_scan_i64(sc_ctx* ctx, const long long* in, long long* out, size_t n, DBuf<char>& tmp);
 int sc_exclusive_scan_i32_to_i64(sc_ctx* ctx, const int* in, long long* out, size_t n, DBuf<char>& tmp);
 int sc_sort_pairs_u64_f64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, double* vals_in,
-                          double* vals_out, size_t n, int end_bit, DBuf<char>& tmp);
+                          double* vals_out, size_t n, int end_bit, DBuf<char>& tmp, int begin_bit = 0);
 int sc_sort_pairs_u64_u32(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, unsigned* vals_in,
                           unsigned* vals_out, size_t n, int end_bit, DBuf<char>& tmp);
 int sc_sort_keys_u64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, size_t n, int end_bit,

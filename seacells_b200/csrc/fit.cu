@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "comm.cuh"
 #include "fit_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -106,6 +107,150 @@ __global__ void k_lists_from_sorted(int rows, long long total, const unsigned lo
     }
     len[t] = (int)(lo2 - lo);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ products with K
+// K = M M^T is formed once per kernel matrix (cpu.py:128,157 `self.K = M @ M.T`), rows in first-occurrence order with
+// K[i,p] = sum_q M[i,q] M[q,p] accumulated over q ascending.  K is bitwise symmetric (M is; the products commute; the
+// order is the same), so column p of K is row p.  A product K X with a column-sparse X (B: ~14 entries per column; the
+// one-hot E_t of one Frank-Wolfe step: 1 per column) is evaluated in "push" form: every source entry X[c, a] = w sends
+// w K[c, i] to (cell i, archetype a) for the stored entries of row c of K, the triples are grouped by a stable radix
+// sort on (cell, archetype) and runs of equal (cell, archetype) are summed in emission order (ascending archetype, then
+// slot) - a fixed order, so the result is bitwise reproducible and independent of how the cells are sharded.
+// The work is proportional to the number of sources x ~400, not to n x (row work): 5 M triples for one step's K E_t at
+// 1M cells, where the row-wise two-stage product M (M E_t) launched over all n rows cost 1.5 ms per step.
+struct PushSrc {
+  int m;                  // sources
+  const int* cell;        // [m] source cell c
+  const int* key;         // [m] archetype a, or null: a = source index
+  const double* w;        // [m] weight, or null: 1.0
+};
+// which target cells are kept: this rank's slab [r0, r1) plus cells whose bit is set in `extra` (may be null)
+struct PushFilter {
+  int r0, r1;
+  const unsigned* extra;
+};
+__device__ __forceinline__ bool push_keep(const PushFilter& f, int i) {
+  return (i >= f.r0 && i < f.r1) || (f.extra && ((f.extra[i >> 5] >> (i & 31)) & 1u));
+}
+__global__ void __launch_bounds__(256) k_push_count(PushSrc src, RowLists K, PushFilter f, int* __restrict__ cnt) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s > src.m) return;
+  if (s == src.m) {
+    if (lane == 0) cnt[s] = 0;  // so that the exclusive scan over m + 1 values ends with the total
+    return;
+  }
+  const int c = src.cell[s];
+  const long long p = K.ptr[c];
+  const int L = K.len[c];
+  int tot = 0;
+  for (int x0 = 0; x0 < L; x0 += 32) {
+    const bool keep = (x0 + lane < L) && push_keep(f, K.key[p + x0 + lane]);
+    tot += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  if (lane == 0) cnt[s] = tot;
+}
+__global__ void __launch_bounds__(256)
+k_push_emit(PushSrc src, RowLists K, PushFilter f, const long long* __restrict__ off, int kbits,
+            unsigned long long* __restrict__ keys, double* __restrict__ vals) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= src.m) return;
+  const int c = src.cell[s];
+  const unsigned long long a = (unsigned long long)(unsigned)(src.key ? src.key[s] : s);
+  const bool weighted = src.w != nullptr;
+  const double w = weighted ? src.w[s] : 1.0;
+  const long long p = K.ptr[c];
+  const int L = K.len[c];
+  long long o = off[s];
+  for (int x0 = 0; x0 < L; x0 += 32) {
+    int i = 0;
+    bool keep = false;
+    if (x0 + lane < L) {
+      i = K.key[p + x0 + lane];
+      keep = push_keep(f, i);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const long long pos = o + __popc(ball & ((1u << lane) - 1u));
+      keys[pos] = ((unsigned long long)(unsigned)i << kbits) | a;
+      const double kv = K.val[p + x0 + lane];
+      vals[pos] = weighted ? __dmul_rn(w, kv) : kv;
+    }
+    o += __popc(ball);
+  }
+}
+// sorted triples -> row lists.  heads[e] = 1 where a new (cell, archetype) run starts.
+__global__ void k_run_heads(long long total, const unsigned long long* __restrict__ keys, long long* __restrict__ heads) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > total) return;
+  heads[e] = (e < total && (e == 0 || keys[e] != keys[e - 1])) ? 1 : 0;  // heads[total] = 0: the scan ends with the count
+}
+// one thread per run head: sum the run in order, write the compacted (cell-keyed) entry
+__global__ void k_run_sum(long long total, const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
+                          const long long* __restrict__ pos, int kbits, unsigned long long* __restrict__ ckeys,
+                          int* __restrict__ out_key, double* __restrict__ out_val) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const unsigned long long key = keys[e];
+  if (e > 0 && keys[e - 1] == key) return;
+  double acc = vals[e];
+  for (long long x = e + 1; x < total && keys[x] == key; ++x) acc = __dadd_rn(acc, vals[x]);
+  const long long o = pos[e];
+  ckeys[o] = key;
+  out_key[o] = (int)(key & ((1ull << kbits) - 1ull));
+  out_val[o] = acc;
+}
+// row bounds of the compacted, (cell << kbits | archetype)-sorted entries; `total` is read from device memory
+__global__ void k_rows_from_ckeys(int rows, const long long* __restrict__ total_dev,
+                                  const unsigned long long* __restrict__ ckeys, int kbits, long long* __restrict__ ptr,
+                                  int* __restrict__ len) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > rows) return;
+  const long long total = *total_dev;
+  auto lower = [&](unsigned long long target) {
+    long long lo = 0, hi = total;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (ckeys[mid] < target) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  const long long lo = lower((unsigned long long)(unsigned)t << kbits);
+  ptr[t] = lo;
+  if (t < rows) len[t] = (int)(lower((unsigned long long)(unsigned)(t + 1) << kbits) - lo);
+}
+__global__ void k_unpack_low(long long total, const unsigned long long* __restrict__ keys, int kbits, int* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < total) out[e] = (int)(keys[e] & ((1ull << kbits) - 1ull));
+}
+// B slots -> push sources (archetype-major, slot order)
+__global__ void k_b_sources(int k, int S, const int* __restrict__ b_idx, const double* __restrict__ b_val,
+                            const int* __restrict__ b_cnt, const long long* __restrict__ off, int* __restrict__ cell,
+                            int* __restrict__ key, double* __restrict__ w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * S) return;
+  const int a = e / S, sl = e - a * S;
+  if (sl >= b_cnt[a]) return;
+  const long long o = off[a] + sl;
+  cell[o] = b_idx[e];
+  key[o] = a;
+  w[o] = b_val[e];
+}
+__global__ void k_b_support_bits(int k, int S, const int* __restrict__ b_idx, const int* __restrict__ b_cnt,
+                                 unsigned* __restrict__ bits) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * S) return;
+  const int a = e / S, sl = e - a * S;
+  if (sl >= b_cnt[a]) return;
+  const int c = b_idx[e];
+  atomicOr(&bits[c >> 5], 1u << (c & 31));
+}
+__global__ void k_csr_as_lists(int n, const int* __restrict__ indptr, long long* __restrict__ ptr, int* __restrict__ len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  ptr[i] = indptr[i];
+  if (i < n) len[i] = indptr[i + 1] - indptr[i];
 }
 
 // t1A[i'][i] = sum over slots (cell, b) of B[:, i'] of b * KB[cell, i]      (cpu.py:442  t1 = t2 @ B)
@@ -629,6 +774,10 @@ struct UpdBArgs {
 constexpr int UPB_CHUNK = 1024;  // candidates per CTA
 __device__ __forceinline__ void block_argmin_256(double& v, int& i, double* sg, int* si);
 
+__global__ void k_cand_counts(int k, const long long* __restrict__ c_ptr, long long* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < k) out[a] = c_ptr[a + 1] - c_ptr[a];
+}
 __global__ void k_chunk_count(int k, const long long* __restrict__ c_ptr, const int* __restrict__ hub_slot,
                               int* __restrict__ nch) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1294,11 +1443,11 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
 
 // ------------------------------------------------------------------------------------------------ RSS, labels
 // out[j] = a_j^T t1A a_j - 2 <KB[j,:], a_j>     (||M - M B A||_F^2 = ||M||_F^2 + sum_j out[j])
-__global__ void k_rss_cell(int n, int k, int S, const int* __restrict__ a_idx, const double* __restrict__ a_val,
+__global__ void k_rss_cell(int r0, int r1, int k, int S, const int* __restrict__ a_idx, const double* __restrict__ a_val,
                            const int* __restrict__ a_cnt, RowLists KB, const double* __restrict__ t1T,
                            double* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
+  const int warp = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= r1) return;
   const int j = warp;
   const int cnt = a_cnt[j];
   const int* idx = a_idx + (size_t)j * S;
@@ -1399,20 +1548,19 @@ void sc_fit::pstop(int stage) {
   cudaStreamSynchronize(ctx->stream);
   prof[stage] += now_s() - prof_t0;
 }
-static int set_smem_attr_once(sc_ctx* ctx) {
-  static bool done = false;
-  if (done) return SC_OK;
+static int set_smem_attr_once(sc_ctx* ctx) {  // per device, so once per engine
   SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(FWA_PER_WARP * FWA_WARPS)));
   SC_CUDA(ctx, cudaFuncSetAttribute(k_updateA_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(FWA_PER_WARP * FWA_WARPS)));
-  done = true;
   return SC_OK;
 }
 
 sc_fit::~sc_fit() {
   for (auto e : ev_a) cudaEventDestroy(e);
   for (auto e : ev_b) cudaEventDestroy(e);
+  for (auto e : ev_h0) cudaEventDestroy(e);
+  for (auto e : ev_h1) cudaEventDestroy(e);
 }
 
 int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
@@ -1424,6 +1572,14 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   n = n_;
   row_begin = 0;
   row_end = n_;
+  slab = n_;
+  if (ctx->world() > 1) {  // contiguous, equal slabs of cells; the last ranks may own a short or empty slab
+    const int w = ctx->world();
+    if (w > 64) SC_FAIL(ctx, SC_ERR_ARG, "fit: at most 64 ranks");
+    slab = (n_ + w - 1) / w;
+    row_begin = std::min(n_, ctx->rank() * slab);
+    row_end = std::min(n_, row_begin + slab);
+  }
   k = k_;
   T = T_;
   S = std::max(T_, 1);
@@ -1441,7 +1597,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   SC_TRY(b_cnt.ensure(ctx, (size_t)k));
   SC_TRY(t1A.ensure(ctx, (size_t)k * k));
   SC_TRY(t1B.ensure(ctx, (size_t)k * k));
-  SC_TRY(percell.ensure(ctx, (size_t)std::max(n, 1024)));
+  SC_TRY(percell.ensure(ctx, (size_t)std::max(n, 1024) + 64));
   SC_TRY(scalars.ensure(ctx, 8));
   SC_TRY(slow_list.ensure(ctx, (size_t)n));
   SC_TRY(slow_cnt.ensure(ctx, 4));
@@ -1479,6 +1635,15 @@ int sc_fit::set_kernel(const int* indptr, const int* indices, const double* data
   SC_TRY(sc_sum_f64(ctx, sq.p, scalars.p, (size_t)nnz, tmp));
   SC_CUDA(ctx, cudaMemcpyAsync(&m_fro2, scalars.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // K = M M^T (cpu.py:128,157), rows in first-occurrence order; see "products with K" above
+  {
+    CsrView M{n, m_ptr.p, m_col.p, m_val.p};
+    SC_TRY(m_ptr64.ensure(ctx, (size_t)n + 1));
+    SC_TRY(m_len.ensure(ctx, (size_t)n + 1));
+    SC_LAUNCH(ctx, k_csr_as_lists, (n + 256) / 256, 256, 0, n, m_ptr.p, m_ptr64.p, m_len.p);
+    RowLists Ml{m_ptr64.p, m_len.p, m_col.p, m_val.p};
+    SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Ml, n, Kl, sp, false, true));
+  }
   have_M = true;
   pre_valid = false;
   return SC_OK;
@@ -1554,40 +1719,88 @@ RowLists sc_fit::A_view() const {
   return RowLists{slot_ptr_n.p, a_cnt[a_cur].p, a_idx[a_cur].p, a_val[a_cur].p};
 }
 
-// KB rows and t1A for the current B (shared by _updateA and compute_RSS)
-int sc_fit::compute_KB(int r0, int r1, bool sorted) {
-  CsrView M{n, m_ptr.p, m_col.p, m_val.p};
-  // B by cell
+// Z[i, :] = sum over the sources (c, a, w) of w K[c, i] for the kept cells i; rows come out sorted by archetype.
+// has_dups: several sources may share (i, a) (K B: the members of archetype a within two hops of i) and are summed in
+// source order; the one-hot E_t of a Frank-Wolfe step has one source per archetype, so nothing needs summing.
+int sc_fit::push_product(const PushSrc& src, const PushFilter& f, bool has_dups, RowListsBuf& Z) {
+  const int m = src.m;
+  int kbits = 1, nbits = 1;
+  while ((1ll << kbits) < k) kbits++;
+  while ((1ll << nbits) < n) nbits++;
+  RowLists Kv = Kl.view();
+  SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
+  SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
+  SC_TRY(Z.ptr.ensure(ctx, (size_t)n + 1));
+  SC_TRY(Z.len.ensure(ctx, (size_t)n + 1));
+  Z.rows = n;
+  const unsigned wgrid = (unsigned)((((size_t)m + 1) * 32 + 255) / 256);
+  SC_LAUNCH(ctx, k_push_count, wgrid, 256, 0, src, Kv, f, ps_cnt.p);
+  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
+  long long total = 0;
+  SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  last_push_total = total;
+  SC_TRY(pk_keys_in.ensure(ctx, (size_t)total + 1));
+  SC_TRY(pk_keys_out.ensure(ctx, (size_t)total + 1));
+  SC_TRY(pv_in.ensure(ctx, (size_t)total + 1));
+  SC_TRY(Z.key.ensure(ctx, (size_t)total + 1));
+  SC_TRY(Z.val.ensure(ctx, (size_t)total + 1));
+  if (total == 0) {
+    SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
+    SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+    return SC_OK;
+  }
+  SC_LAUNCH(ctx, k_push_emit, wgrid, 256, 0, src, Kv, f, ps_off.p, kbits, pk_keys_in.p, pv_in.p);
+  const unsigned egrid = (unsigned)((total + 256) / 256);
+  if (!has_dups) {
+    // stable sort on the cell bits only: inside a cell the emission order (ascending archetype) is kept
+    SC_TRY(sc_sort_pairs_u64_f64(ctx, pk_keys_in.p, pk_keys_out.p, pv_in.p, Z.val.p, (size_t)total, kbits + nbits, tmp,
+                                 kbits));
+    SC_LAUNCH(ctx, k_unpack_low, egrid, 256, 0, total, pk_keys_out.p, kbits, Z.key.p);
+    SC_LAUNCH(ctx, k_rows_from_ckeys, (n + 256) / 256, 256, 0, n, ps_off.p + m, pk_keys_out.p, kbits, Z.ptr.p, Z.len.p);
+    return SC_OK;
+  }
+  SC_TRY(pv_out.ensure(ctx, (size_t)total + 1));
+  SC_TRY(run_heads.ensure(ctx, (size_t)total + 1));
+  SC_TRY(run_pos.ensure(ctx, (size_t)total + 1));
+  SC_TRY(ckeys.ensure(ctx, (size_t)total + 1));
+  SC_TRY(sc_sort_pairs_u64_f64(ctx, pk_keys_in.p, pk_keys_out.p, pv_in.p, pv_out.p, (size_t)total, kbits + nbits, tmp, 0));
+  SC_LAUNCH(ctx, k_run_heads, egrid, 256, 0, total, pk_keys_out.p, run_heads.p);
+  SC_TRY(sc_exclusive_scan_i64(ctx, run_heads.p, run_pos.p, (size_t)total + 1, tmp));
+  SC_LAUNCH(ctx, k_run_sum, egrid, 256, 0, total, pk_keys_out.p, pv_out.p, run_pos.p, kbits, ckeys.p, Z.key.p, Z.val.p);
+  SC_LAUNCH(ctx, k_rows_from_ckeys, (n + 256) / 256, 256, 0, n, run_pos.p + total, ckeys.p, kbits, Z.ptr.p, Z.len.p);
+  return SC_OK;
+}
+
+// K B rows for the current B (cpu.py:441 `K @ B`), sorted by archetype, for the cells [r0, r1) and - with_support - for
+// the cells of supp(B) wherever they live (t1 = (K B)^T B needs exactly those rows, cpu.py:442)
+int sc_fit::compute_KB(int r0, int r1, bool with_support) {
   pstart();
   const int ks = k * S;
   SC_TRY(b_off.ensure(ctx, (size_t)k + 1));
-  SC_TRY(bk_in.ensure(ctx, (size_t)ks + 1));
-  SC_TRY(bk_out.ensure(ctx, (size_t)ks + 1));
-  SC_TRY(bv_in.ensure(ctx, (size_t)ks + 1));
-  SC_TRY(brow.ptr.ensure(ctx, (size_t)n + 1));
-  SC_TRY(brow.len.ensure(ctx, (size_t)n + 1));
-  SC_TRY(brow.key.ensure(ctx, (size_t)ks + 1));
-  SC_TRY(brow.val.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(src_cell.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(src_key.ensure(ctx, (size_t)ks + 1));
+  SC_TRY(src_w.ensure(ctx, (size_t)ks + 1));
   SC_CUDA(ctx, cudaMemcpyAsync(cnt_k.p, b_cnt.p, sizeof(int) * (size_t)k, cudaMemcpyDeviceToDevice, ctx->stream));
   SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p + k, 0, sizeof(int), ctx->stream));
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_k.p, b_off.p, (size_t)k + 1, tmp));
   long long bnnz = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&bnnz, b_off.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-  SC_LAUNCH(ctx, k_emit_b_pairs, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_val.p, b_cnt.p, b_off.p, bk_in.p, bv_in.p);
+  SC_LAUNCH(ctx, k_b_sources, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_val.p, b_cnt.p, b_off.p, src_cell.p, src_key.p,
+            src_w.p);
+  PushFilter f{r0, r1, nullptr};
+  if (with_support && !(r0 == 0 && r1 == n)) {
+    const size_t words = ((size_t)n + 31) / 32;
+    SC_TRY(supp_bits.ensure(ctx, words));
+    SC_CUDA(ctx, cudaMemsetAsync(supp_bits.p, 0, sizeof(unsigned) * words, ctx->stream));
+    SC_LAUNCH(ctx, k_b_support_bits, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_cnt.p, supp_bits.p);
+    f.extra = supp_bits.p;
+  }
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  int nbits = 1;
-  while ((1ll << nbits) < n) nbits++;
-  SC_TRY(sc_sort_pairs_u64_f64(ctx, bk_in.p, bk_out.p, bv_in.p, brow.val.p, (size_t)bnnz, 32 + nbits, tmp));
-  const long long span = std::max<long long>(bnnz, (long long)n + 1);
-  SC_LAUNCH(ctx, k_lists_from_sorted, (unsigned)((span + 255) / 256), 256, 0, n, bnnz, bk_out.p, brow.ptr.p, brow.len.p,
-            brow.key.p);
-  RowLists Bl = brow.view();
   pstop(P_BROW);
   pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Bl, k, Y, sp, sorted));
-  pstop(P_SPGEMM_Y);
-  pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, r0, r1, Y.view(), k, KB, sp, sorted));
+  PushSrc src{(int)bnnz, src_cell.p, src_key.p, src_w.p};
+  SC_TRY(push_product(src, f, true, KB));
   pstop(P_SPGEMM_KB);
   return SC_OK;
 }
@@ -1605,29 +1818,14 @@ static void swap_lists(RowListsBuf& a, RowListsBuf& b) {
 }
 
 // K B_t from K B_{t-1} and the cells chosen at step t-1 (amin_cur, written by k_updateB_step):
-//   K B_t = (1 - gamma_{t-1}) K B_{t-1} + gamma_{t-1} M (M E_{t-1}),   gamma_0 = 1 (B was reset to E_0)
+//   K B_t = (1 - gamma_{t-1}) K B_{t-1} + gamma_{t-1} K E_{t-1},   gamma_0 = 1 (B was reset to E_0)
 int sc_fit::advance_KB(int t) {
-  CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   pstart();
-  SC_TRY(bk_in.ensure(ctx, (size_t)k + 1));
-  SC_TRY(bk_out.ensure(ctx, (size_t)k + 1));
-  SC_TRY(erow.ptr.ensure(ctx, (size_t)n + 1));
-  SC_TRY(erow.len.ensure(ctx, (size_t)n + 1));
-  SC_TRY(erow.key.ensure(ctx, (size_t)k + 1));
-  SC_TRY(erow.val.ensure(ctx, (size_t)k + 1));
-  SC_LAUNCH(ctx, k_emit_e_pairs, (k + 255) / 256, 256, 0, k, amin_cur.p, bk_in.p, erow.val.p);
-  int nbits = 1;
-  while ((1ll << nbits) < n) nbits++;
-  SC_TRY(sc_sort_keys_u64(ctx, bk_in.p, bk_out.p, (size_t)k, 32 + nbits, tmp));
-  const long long span = std::max<long long>(k, (long long)n + 1);
-  SC_LAUNCH(ctx, k_lists_from_sorted, (unsigned)((span + 255) / 256), 256, 0, n, (long long)k, bk_out.p, erow.ptr.p,
-            erow.len.p, erow.key.p);
-  pstop(P_BROW);
-  pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, erow.view(), k, EY, sp, false));
+  PushSrc src{k, amin_cur.p, nullptr, nullptr};
+  PushFilter f{row_begin, row_end, nullptr};
+  SC_TRY(push_product(src, f, false, DKB));
   pstop(P_SPGEMM_Y);
   pstart();
-  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, EY.view(), k, DKB, sp, false));
   if (t == 1) {
     swap_lists(KB, DKB);  // gamma_0 = 1
   } else {
@@ -1676,7 +1874,7 @@ int sc_fit::build_perm() {
 int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
-  SC_TRY(compute_KB(0, n, true));  // all rows, key-sorted (lookups): t1 and the RSS need K B at every cell (replicated across ranks)
+  SC_TRY(compute_KB(row_begin, row_end, true));  // this rank's cells (candidates of _updateA, RSS) + supp(B) (t1)
   pstart();
   SC_CUDA(ctx, cudaMemsetAsync(t1A.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
   SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p, KB.view(), t1A.p);
@@ -1735,7 +1933,19 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   pstop(P_UPDA_SLOW);
   a_cur = nxt;
   a_is_slots = true;
+  // every rank needs all of A for A A^T and K A^T: all-gather the slot arrays (equal slabs, in place)
+  SC_TRY(exchange(a_idx[nxt].p, sizeof(int) * (size_t)slab * S));
+  SC_TRY(exchange(a_val[nxt].p, sizeof(double) * (size_t)slab * S));
+  SC_TRY(exchange(a_cnt[nxt].p, sizeof(int) * (size_t)slab));
   return SC_OK;
+}
+
+// in-place all-gather of equal slabs over the ranks of the job (no-op on one GPU)
+int sc_fit::exchange(void* buf, size_t bytes_per_rank) {
+  if (!ctx->comm || ctx->comm->world == 1) return SC_OK;
+  const int rc = ctx->comm->allgather(buf, bytes_per_rank, ctx->stream);
+  if (rc != SC_OK) ctx->err = ctx->comm->err;
+  return rc;
 }
 
 int sc_fit::update_B_begin() {
@@ -1840,17 +2050,25 @@ int sc_fit::update_B_begin() {
     SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
               c_t2.p);
   }
-  // hub block: archetypes whose candidate list covers more than a quarter of this rank's cells (at most HUB_MAX)
+  // hub block: archetypes whose candidate list covers more than a quarter of all cells (at most hub_cap of them).  The
+  // choice is made on the candidate counts summed over the ranks, so every rank routes an archetype through the same
+  // kernel and a column's gradients are the same numbers however the cells are sharded.
   {
     const int nloc = row_end - row_begin;
-    std::vector<long long> hc((size_t)k + 1);
-    SC_CUDA(ctx, cudaMemcpyAsync(hc.data(), c_ptr.p, sizeof(long long) * ((size_t)k + 1), cudaMemcpyDeviceToHost,
+    const int w = ctx->world();
+    SC_TRY(cand_cnt.ensure(ctx, (size_t)w * k));
+    SC_LAUNCH(ctx, k_cand_counts, (k + 255) / 256, 256, 0, k, c_ptr.p, cand_cnt.p + (size_t)ctx->rank() * k);
+    SC_TRY(exchange(cand_cnt.p, sizeof(long long) * (size_t)k));
+    std::vector<long long> hall((size_t)w * k), hc((size_t)k, 0);
+    SC_CUDA(ctx, cudaMemcpyAsync(hall.data(), cand_cnt.p, sizeof(long long) * hall.size(), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < w; ++r)
+      for (int a = 0; a < k; ++a) hc[a] += hall[(size_t)r * k + a];
     std::vector<std::pair<long long, int>> big;
-    const long long thr = std::max<long long>(4096, nloc / 4);
+    const long long thr = std::max<long long>(4096, n / 4);
     for (int a = 0; a < k; ++a)
-      if (hc[a + 1] - hc[a] > thr) big.push_back({-(hc[a + 1] - hc[a]), a});
+      if (hc[a] > thr) big.push_back({-hc[a], a});
     std::sort(big.begin(), big.end());
     if ((int)big.size() > hub_cap) big.resize(hub_cap);
     std::vector<int> ids, slot(k, -1);
@@ -1895,7 +2113,7 @@ int sc_fit::update_B_begin() {
   SC_LAUNCH(ctx, k_chunk_fill, k, 128, 0, k, chunk_ptr.p, chunk_arch.p);
   pstop(P_T2TRANS);
   nchunks_cur = nchunks;
-  SC_TRY(part_out.ensure(ctx, (size_t)k * 4));
+  SC_TRY(part_out.ensure(ctx, (size_t)k * 4 * ctx->world()));
   in_update_B = true;
   return SC_OK;
 }
@@ -1905,8 +2123,13 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (t < 0 || t >= T) SC_FAIL(ctx, SC_ERR_ARG, "update_B_eval: bad step");
   // K B for the current B (cpu.py:486), this rank's rows, first-occurrence order (the rows are only walked here):
   // evaluated from B at the first step, then advanced by the step's rank-k change (see k_kb_merge)
-  if (t == 0 || fresh_kb) SC_TRY(compute_KB(row_begin, row_end, false));
-  else SC_TRY(advance_KB(t));
+  if (t == 0) {
+    if (!pre_valid) SC_TRY(compute_KB(row_begin, row_end, false));  // else: the rows _updateA / the RSS just used
+  } else if (fresh_kb) {
+    SC_TRY(compute_KB(row_begin, row_end, false));
+  } else {
+    SC_TRY(advance_KB(t));
+  }
   UpdBArgs g;
   g.n = n;
   g.k = k;
@@ -1952,16 +2175,29 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     const bool inc = !fresh_kb && t >= 2;
     const double gamma = inc ? 2.0 / ((double)(t - 1) + 2.0) : 0.0;
     const RowLists hub_rows = inc ? DKB.view() : KB.view();
+    if ((int)ev_h0.size() <= t) {
+      cudaEvent_t ea, eb;
+      SC_CUDA(ctx, cudaEventCreate(&ea));
+      SC_CUDA(ctx, cudaEventCreate(&eb));
+      ev_h0.push_back(ea);
+      ev_h1.push_back(eb);
+    }
+    if (inc) {  // algorithmic bytes of this launch: HH read + write and t2, 8 B each per (cell, hub), + the delta rows
+      hub_bytes_total += 24.0 * (double)nloc * n_hub + 12.0 * (double)last_push_total;
+      hub_launches_counted++;
+    }
+    SC_CUDA(ctx, cudaEventRecord(ev_h0[t], ctx->stream));
 #define SC_HUB_LAUNCH(RR)                                                                                              \
   SC_LAUNCH(ctx, (k_updateB_hub<RR, (RR <= 2 ? 4 : 2)>), nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, hub_rows, T1H.p, T2H.p, HH.p, \
             inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p)
-    switch (n_hub_pad / 32) {
+    if (nctas > 0) switch (n_hub_pad / 32) {
       case 1: SC_HUB_LAUNCH(1); break;
       case 2: SC_HUB_LAUNCH(2); break;
       case 3: SC_HUB_LAUNCH(3); break;
       default: SC_HUB_LAUNCH(4); break;
     }
 #undef SC_HUB_LAUNCH
+    SC_CUDA(ctx, cudaEventRecord(ev_h1[t], ctx->stream));
     SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
@@ -2007,6 +2243,11 @@ int sc_fit::update_B_end() {
       SC_CUDA(ctx, cudaEventElapsedTime(&ms, ev_a[t], ev_b[t]));
       eval_ms_total += ms;
       eval_steps++;
+      if (n_hub > 0 && !fresh_kb && t >= 2 && (int)ev_h0.size() > t) {  // incremental launches only (steps 0, 1 evaluate in full)
+        SC_CUDA(ctx, cudaEventElapsedTime(&ms, ev_h0[t], ev_h1[t]));
+        hub_ms_total += ms;
+        hub_steps++;
+      }
     }
     long long kbn = 0;  // nnz(K B) of the last Frank-Wolfe step (this rank's rows)
     SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p + 1, 0, sizeof(unsigned long long), ctx->stream));
@@ -2022,19 +2263,16 @@ int sc_fit::update_B_end() {
 // _updateB on one GPU: the split-phase calls back to back (the multi-GPU host inserts one all-gather per step)
 int sc_fit::update_B(int* trace_dev) {
   SC_TRY(update_B_begin());
+  const int w = ctx->world();
+  const size_t pbytes = sizeof(double) * (size_t)k * 4;
   for (int t = 0; t < T; ++t) {
-    SC_TRY(update_B_eval(t, part_out.p));
-    SC_TRY(update_B_step(t, part_out.p, 1, trace_dev));
+    // this rank's per-archetype {candidate min G, cell, non-candidate G, cell} goes straight into its slab of the gathered
+    // buffer; the all-gather is the north_star's exchange of (value, index) argmin pairs
+    SC_TRY(update_B_eval(t, part_out.p + (size_t)ctx->rank() * k * 4));
+    SC_TRY(exchange(part_out.p, pbytes));
+    SC_TRY(update_B_step(t, part_out.p, w, trace_dev));
   }
   return update_B_end();
-}
-
-int sc_fit::set_shard(int r0, int r1) {
-  if (r0 < 0 || r1 > n || r0 > r1) SC_FAIL(ctx, SC_ERR_ARG, "set_shard: bad cell range");
-  row_begin = r0;
-  row_end = r1;
-  pre_valid = false;
-  return SC_OK;
 }
 
 int sc_fit::rss(double* out_host) {
@@ -2042,8 +2280,13 @@ int sc_fit::rss(double* out_host) {
   SC_TRY(precompute_A());
   const int cur = a_cur;
   pstart();
-  SC_LAUNCH(ctx, k_rss_cell, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, k, S, a_idx[cur].p, a_val[cur].p,
-            a_cnt[cur].p, KB.view(), t1A.p, percell.p);
+  // per-cell terms on this rank's cells; every rank then sums all n of them in the same fixed order (no floating-point
+  // reduction across ranks: the RSS is bitwise the single-GPU value)
+  const int nloc = row_end - row_begin;
+  if (nloc > 0)
+    SC_LAUNCH(ctx, k_rss_cell, (unsigned)(((size_t)nloc * 32 + 255) / 256), 256, 0, row_begin, row_end, k, S, a_idx[cur].p,
+              a_val[cur].p, a_cnt[cur].p, KB.view(), t1A.p, percell.p);
+  SC_TRY(exchange(percell.p, sizeof(double) * (size_t)slab));
   SC_TRY(sc_sum_f64(ctx, percell.p, scalars.p, (size_t)n, tmp));
   double s = 0.0;
   SC_CUDA(ctx, cudaMemcpyAsync(&s, scalars.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2099,7 +2342,12 @@ __global__ void k_lists_to_csr(int rows, RowLists L, const long long* __restrict
 // K B as CSR (n x k): the transpose of Z_ = B_.T @ K (cpu.py:641).  Pass null pointers to get only nnz.
 int sc_fit::get_KB_csr(long long* nnz_out, long long* indptr, int* indices, double* data) {
   if (!have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: B has not been initialised");
-  SC_TRY(precompute_A());
+  if (row_begin == 0 && row_end == n) {
+    SC_TRY(precompute_A());
+  } else {  // a rank of a sharded job holds K B for its own cells only: evaluate every row for this accessor
+    SC_TRY(compute_KB(0, n, false));
+    pre_valid = false;
+  }
   SC_TRY(t_off.ensure(ctx, (size_t)n + 1));
   SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, KB.len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
   SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));

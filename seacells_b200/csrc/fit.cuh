@@ -9,6 +9,8 @@ struct sc_fit {
   sc_ctx* ctx = nullptr;
   int n = 0, k = 0, T = 50, S = 50;
   int row_begin = 0, row_end = 0;  // cells owned by this rank (whole range on one GPU)
+  int slab = 0;                    // cells per rank (equal slabs; the buffers that are all-gathered are padded to world * slab)
+  int exchange(void* buf, size_t bytes_per_rank);
   long long nchunks_cur = 0;
   bool in_update_B = false;
   DBuf<int> hub_ids, hub_slot, gram_hubof, perm;
@@ -29,14 +31,23 @@ struct sc_fit {
   int a_cur = -1;
   DBuf<long long> slot_ptr_n;
   RowListsBuf a0;
+  // K = M M^T, formed once per kernel matrix (first-occurrence row order), and the scratch of the push products
+  DBuf<long long> m_ptr64;
+  DBuf<int> m_len;
+  RowListsBuf Kl;
+  DBuf<int> ps_cnt, src_cell, src_key;
+  DBuf<double> src_w, pv_in, pv_out;
+  DBuf<long long> ps_off, run_heads, run_pos;
+  DBuf<unsigned long long> pk_keys_in, pk_keys_out, ckeys;
+  DBuf<unsigned> supp_bits;
   // compressed B
   DBuf<int> b_idx, b_cnt;
   DBuf<double> b_val;
-  // B by cell, M*B, K*B
-  RowListsBuf brow, Y, KB;
-  // incremental K B inside one _updateB call: chosen cells of the last step, E by cell, M E, K E, second K B buffer
+  // K*B rows
+  RowListsBuf KB;
+  // incremental K B inside one _updateB call: chosen cells of the last step, K E, second K B buffer
   DBuf<int> amin_cur;
-  RowListsBuf erow, EY, DKB, KB2;
+  RowListsBuf DKB, KB2;
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step
@@ -46,7 +57,7 @@ struct sc_fit {
   DBuf<double> t1A, t1B;
   // _updateB precompute
   RowListsBuf MA, T2c;
-  DBuf<long long> c_ptr, a_off, arow_ptr, chunk_ptr, t_off;
+  DBuf<long long> c_ptr, a_off, arow_ptr, chunk_ptr, t_off, cand_cnt;
   DBuf<unsigned long long> ck_in, ck_out;
   DBuf<unsigned> co_in, co_out;
   DBuf<int> c_cellv;
@@ -58,7 +69,9 @@ struct sc_fit {
   DBuf<unsigned long long> eval_cnt;
   long long last_evaluated = 0;
   // CUDA-event timing of the dominant kernel (k_updateB_eval, both rounds of one Frank-Wolfe step), always on
-  std::vector<cudaEvent_t> ev_a, ev_b;
+  std::vector<cudaEvent_t> ev_a, ev_b, ev_h0, ev_h1;
+  double hub_ms_total = 0.0, hub_bytes_total = 0.0;  // k_updateB_hub alone (incremental launches)
+  long long hub_steps = 0, hub_launches_counted = 0, last_push_total = 0;
   double eval_ms_total = 0.0;
   long long eval_steps = 0;
   long long last_kb_nnz = 0;
@@ -88,10 +101,10 @@ struct sc_fit {
   int set_A_lists(const long long* colptr, const int* idx, const double* val);
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
-  int compute_KB(int r0, int r1, bool sorted);
+  int push_product(const struct PushSrc& src, const struct PushFilter& f, bool has_dups, RowListsBuf& Z);
+  int compute_KB(int r0, int r1, bool with_support);
   int advance_KB(int t);
   int build_perm();
-  int set_shard(int r0, int r1);
   int update_B_begin();
   int update_B_eval(int t, double* partial_dev);
   int update_B_step(int t, const double* gathered_dev, int n_ranks, int* trace_dev);

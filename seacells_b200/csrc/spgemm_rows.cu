@@ -452,7 +452,7 @@ k_spgemm_big(int nbig, const int* __restrict__ big_list, int key_space, const in
 }
 
 int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
-                   RowListsBuf& Z, SpgemmScratch& sc, bool sorted) {
+                   RowListsBuf& Z, SpgemmScratch& sc, bool sorted, bool wide) {
   constexpr int CAP = 512, WARPS = 8;
   const int n = S.n;
   SC_TRY(sc.ub.ensure(ctx, (size_t)n + 1));
@@ -473,27 +473,29 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
   const int rows = row_end - row_begin;
   if (rows <= 0) return SC_OK;
   const size_t smem = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // function attributes are per device: set them on every call (a process may drive several GPUs)
+  SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min((rows + WARPS - 1) / WARPS, 148 * 16);
   if (sorted) {
     SC_LAUNCH(ctx, (k_spgemm_fill<CAP, WARPS>), grid, WARPS * 32, smem, row_begin, row_end, S.indptr, S.indices, S.data,
               X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
   } else {
     const size_t smem_fo = (size_t)WARPS * CAP * (sizeof(double) + sizeof(int) + sizeof(unsigned short));
-    static bool attr_fo = false;
-    if (!attr_fo) {
-      SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill_fo<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_fo));
-      attr_fo = true;
-    }
+    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill_fo<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_fo));
     SC_LAUNCH(ctx, k_spgemm_tiny_fo, std::min((rows + 7) / 8, 148 * 32), 256, 0, row_begin, row_end, S.indptr, S.indices,
               S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p);
-    SC_LAUNCH(ctx, (k_spgemm_fill_fo<CAP, WARPS>), grid, WARPS * 32, smem_fo, row_begin, row_end, S.indptr, S.indices,
-              S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+    if (wide) {
+      constexpr int WCAP = 1024;
+      const size_t smem_w = (size_t)WARPS * WCAP * (sizeof(double) + sizeof(int) + sizeof(unsigned short));
+      SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_fill_fo<WCAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_w));
+      SC_LAUNCH(ctx, (k_spgemm_fill_fo<WCAP, WARPS>), grid, WARPS * 32, smem_w, row_begin, row_end, S.indptr, S.indices,
+                S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+    } else {
+      SC_LAUNCH(ctx, (k_spgemm_fill_fo<CAP, WARPS>), grid, WARPS * 32, smem_fo, row_begin, row_end, S.indptr, S.indices,
+                S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.big_list.p);
+    }
   }
   int nbig = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&nbig, sc.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -27,13 +27,13 @@ int sc_exclusive_scan_i32_to_i64(sc_ctx* ctx, const int* in, long long* out, siz
 }
 
 int sc_sort_pairs_u64_f64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, double* vals_in,
-                          double* vals_out, size_t n, int end_bit, DBuf<char>& tmp) {
+                          double* vals_out, size_t n, int end_bit, DBuf<char>& tmp, int begin_bit) {
   size_t bytes = 0;
-  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n, 0,
-                                               end_bit, ctx->stream));
+  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n,
+                                               begin_bit, end_bit, ctx->stream));
   SC_TRY(tmp.ensure(ctx, bytes));
-  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n, 0,
-                                               end_bit, ctx->stream));
+  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n,
+                                               begin_bit, end_bit, ctx->stream));
   ctx->launches += 1;
   return SC_OK;
 }

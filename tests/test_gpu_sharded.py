@@ -1,5 +1,6 @@
-"""The row-sharded (multi-GPU) code path: emulated on one GPU in-process, and for real over NCCL when >= 2 GPUs exist."""
-import ctypes as C
+"""The row-sharded (multi-GPU) code path.  The exchange lives in the library (comm.cuh): here it runs with ranks as
+threads of one process on a single GPU (LocalComm) and, when >= 2 GPUs exist, with one process per GPU over NCCL.
+The sharded fit must equal the reference's golden vectors and the single-GPU fit bit for bit."""
 import os
 
 import numpy as np
@@ -12,108 +13,91 @@ from tests.helpers import csr_from, load_golden, same_sparse
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_fit(g, world):
-    """`world` engines on one GPU, each owning a slab of cells; the two exchanges are done by hand with torch copies."""
-    import torch
-    from seacells_b200 import FitEngine
-    from seacells_b200.parallel import device_view, slab_range, slab_size
-    M = csr_from(g, "M")
-    n, k, T = M.shape[0], int(g["k"]), int(g["T"])
-    A0 = O.l1_normalise_columns(csr_from(g, "A0"))
-    engs = []
-    for r in range(world):
-        e = FitEngine(n, k, T)
-        e.set_kernel(M)
-        e.set_archetypes(g["archetypes"])
-        e.set_A(A0)
-        b, en = slab_range(r, world, n)
-        e.ctx.check(e.ctx.lib.sc_fit_set_shard(e.h, b, en), "set_shard")
-        engs.append(e)
-    lib, ctx = engs[0].ctx.lib, engs[0].ctx
-    S, c = engs[0].S, slab_size(n, world)
+def _local_fit(M, k, T, arch, A0n, world, n_iter, X=None, devices=None):
+    """`world` ranks as threads; every rank holds the same inputs and makes the same calls.  Returns per-rank results."""
+    from seacells_b200 import FitEngine, build_kernel
+    from seacells_b200.parallel import LocalGroup
+    grp = LocalGroup(world, devices)
+    n = M.shape[0]
 
-    def slots(e):
-        pi, pv, pc, rows = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_longlong()
-        ctx.check(lib.sc_fit_A_slots_device(e.h, C.byref(pi), C.byref(pv), C.byref(pc), C.byref(rows)), "slots")
-        R = int(rows.value)
-        return (device_view(pi.value, (R, S), torch.int32), device_view(pv.value, (R, S), torch.float64),
-                device_view(pc.value, (R,), torch.int32))
+    def work(rank, ctx):
+        out = {}
+        if X is not None:   # sharded kernel construction: every rank searches its own query slab
+            km = build_kernel(X, 15, "union", ctx)
+            out["M"], out["sigma"], out["idx"], out["d2"] = km.export()
+            km.close()
+        eng = FitEngine(n, k, T, ctx)
+        out["shard"] = eng.shard()
+        eng.set_kernel(M)
+        eng.set_archetypes(arch)
+        eng.set_A(A0n)
+        rss, it, conv, thr = eng.run(max_iter=n_iter, min_iter=n_iter)
+        out.update(rss=rss, A=eng.A(), B=eng.B(), labels=eng.hard_assignments(), KB=eng.KB(), hubs=eng.stats()[
+            "hub_archetypes_last_update_B"])
+        eng.close()
+        return out
 
-    def update_A():
-        for e in engs:
-            e.update_A(0.0)
-        ctx.sync()
-        views = [slots(e) for e in engs]
-        for r in range(world):          # "all-gather": every engine receives every other engine's slab
-            b, en = slab_range(r, world, n)
-            for q in range(world):
-                if q != r:
-                    for dst, src in zip(views[q], views[r]):
-                        dst[b:en].copy_(src[b:en])
-        torch.cuda.synchronize()
-
-    def update_B():
-        parts = [torch.zeros(k * 4, dtype=torch.float64, device="cuda") for _ in engs]
-        for e in engs:
-            ctx.check(lib.sc_fit_update_B_begin(e.h), "begin")
-        for t in range(T):
-            for e, p in zip(engs, parts):
-                ctx.check(lib.sc_fit_update_B_eval(e.h, t, C.c_void_p(p.data_ptr())), "eval")
-            ctx.sync()
-            gathered = torch.cat(parts).contiguous()
-            torch.cuda.synchronize()
-            for e in engs:
-                ctx.check(lib.sc_fit_update_B_step(e.h, t, C.c_void_p(gathered.data_ptr()), world), "step")
-            ctx.sync()
-        for e in engs:
-            ctx.check(lib.sc_fit_update_B_end(e.h), "end")
-
-    update_A()
-    rss = [engs[0].rss()]
-    for it in range(int(g["n_iter"])):
-        update_A()
-        update_B()
-        r = [e.rss() for e in engs]
-        assert len(set(r)) == 1, "replicated RSS must agree bit for bit across ranks"
-        rss.append(r[0])
-    return engs, rss
+    try:
+        return grp.run(work)
+    finally:
+        grp.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_emulated_shards_reproduce_the_reference(world):
+def test_local_ranks_reproduce_the_reference(world):
     g = load_golden("rna_n600_k8_sparse")
-    engs, rss = _emulated_fit(g, world)
-    np.testing.assert_allclose(rss, g["RSS_iters"], rtol=1e-9)
-    for e in engs:
-        assert same_sparse(e.A(), csr_from(g, "A_final"))
-        assert same_sparse(e.B(), csr_from(g, "B_final"))
-        assert np.array_equal(e.hard_assignments(), g["labels"])
+    M = csr_from(g, "M")
+    res = _local_fit(M, int(g["k"]), int(g["T"]), g["archetypes"], O.l1_normalise_columns(csr_from(g, "A0")), world,
+                     int(g["n_iter"]), X=g["X32"])
+    from seacells_b200.parallel import slab_range
+    for r, out in enumerate(res):
+        assert out["shard"] == slab_range(r, world, M.shape[0])
+        np.testing.assert_allclose(out["rss"], g["RSS_iters"], rtol=1e-9)
+        assert out["rss"] == res[0]["rss"], "the RSS must agree bit for bit across ranks"
+        assert same_sparse(out["A"], csr_from(g, "A_final"))
+        assert same_sparse(out["B"], csr_from(g, "B_final"))
+        assert np.array_equal(out["labels"], g["labels"])
+        # sharded kernel construction: same kNN graph and kernel matrix on every rank
+        D = O.knn_distance_graph(out["idx"], out["d2"], M.shape[0])
+        assert same_sparse(D, csr_from(g, "D"))
+        assert np.array_equal(out["M"].indices, M.indices)
+        np.testing.assert_allclose(out["M"].data, M.data, rtol=1e-13, atol=0)
+        assert same_sparse(out["KB"], res[0]["KB"])  # the Z_ accessor evaluates every row on every rank
 
 
-def test_emulated_shards_with_hub_archetypes():
-    """5000 cells: hub archetypes exist, so the cell-major hub block and the per-rank hub selection are exercised;
-    the sharded result must equal the single-engine result bit for bit."""
+def test_local_ranks_with_hub_archetypes():
+    """5000 cells: hub archetypes exist, so the cell-major hub block and the job-wide hub selection are exercised; the
+    sharded result must equal the single-engine result bit for bit."""
     from seacells_b200 import FitEngine
     from seacells_b200.synth import synth_archetypes, synth_assignments, synth_embedding
     n, k = 5000, 66
     X = synth_embedding(n, 50, 0)
     M, *_ = O.build_kernel(X.astype(np.float64), 15)
-    arch, A0 = synth_archetypes(n, k), synth_assignments(n, k)
-    g = {"M_data": M.data, "M_indices": M.indices.astype(np.int32), "M_indptr": M.indptr.astype(np.int64),
-         "M_shape": np.array(M.shape), "k": k, "T": 50, "archetypes": arch, "n_iter": 2}
-    A0c = sp.csr_matrix(A0)
-    g.update({"A0_data": A0c.data, "A0_indices": A0c.indices.astype(np.int32), "A0_indptr": A0c.indptr.astype(np.int64),
-              "A0_shape": np.array(A0c.shape)})
-    engs, rss = _emulated_fit(g, 3)
+    arch, A0n = synth_archetypes(n, k), O.l1_normalise_columns(synth_assignments(n, k))
+    res = _local_fit(M, k, 50, arch, A0n, 3, 2)
     one = FitEngine(n, k)
     one.set_kernel(M)
     one.set_archetypes(arch)
-    one.set_A(O.l1_normalise_columns(A0))
+    one.set_A(A0n)
     rss1, *_ = one.run(max_iter=2, min_iter=2)
     assert one.stats()["hub_archetypes_last_update_B"] > 0
-    assert rss == rss1
-    for e in engs:
-        assert same_sparse(e.A(), one.A()) and same_sparse(e.B(), one.B())
+    for out in res:
+        assert out["hubs"] == one.stats()["hub_archetypes_last_update_B"]
+        assert out["rss"] == rss1
+        assert same_sparse(out["A"], one.A()) and same_sparse(out["B"], one.B())
+
+
+def test_local_ranks_on_two_devices():
+    """The thread transport also drives several GPUs from one process (peer copies)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    g = load_golden("atac_n900_k12_sparse")
+    M = csr_from(g, "M")
+    res = _local_fit(M, int(g["k"]), int(g["T"]), g["archetypes"], O.l1_normalise_columns(csr_from(g, "A0")), 2,
+                     int(g["n_iter"]), devices=[0, 1])
+    for out in res:
+        assert same_sparse(out["A"], csr_from(g, "A_final")) and same_sparse(out["B"], csr_from(g, "B_final"))
 
 
 def _nccl_worker(rank, world, port, name, ret):
@@ -123,20 +107,22 @@ def _nccl_worker(rank, world, port, name, ret):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    from seacells_b200 import FitEngine, _lib
-    from seacells_b200.parallel import ShardedFit, sharded_knn
+    from seacells_b200 import FitEngine, _lib, build_kernel
+    from seacells_b200.parallel import init_nccl
     g = load_golden(name)
-    ctx = _lib.default_context(rank)
-    idx, d2 = sharded_knn(g["X32"], 15, ctx)
+    ctx = init_nccl(_lib.default_context(rank))
+    assert (ctx.rank, ctx.world) == (rank, world)
+    km = build_kernel(g["X32"], 15, "union", ctx)      # query slabs sharded, all-gathered on the device
+    Mb, sigma, idx, d2 = km.export()
     io, do = O.knn_exact(g["X32"], 15)
     ok = np.array_equal(idx, io) and np.array_equal(d2, do)
     M = csr_from(g, "M")
+    ok = ok and np.array_equal(Mb.indices, M.indices)
     eng = FitEngine(M.shape[0], int(g["k"]), int(g["T"]), ctx)
     eng.set_kernel(M)
     eng.set_archetypes(g["archetypes"])
     eng.set_A(O.l1_normalise_columns(csr_from(g, "A0")))
-    sf = ShardedFit(eng)
-    rss, n_iter, conv, _ = sf.run(max_iter=int(g["max_iter"]), min_iter=int(g["min_iter"]), eps=float(g["eps"]))
+    rss, n_iter, conv, _ = eng.run(max_iter=int(g["max_iter"]), min_iter=int(g["min_iter"]), eps=float(g["eps"]))
     ok = ok and n_iter == int(g["n_iter"]) and np.allclose(rss, g["RSS_iters"], rtol=1e-9)
     ok = ok and same_sparse(eng.A(), csr_from(g, "A_final")) and same_sparse(eng.B(), csr_from(g, "B_final"))
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -157,6 +157,8 @@ int sc_sort_pairs_u64_f64(sc_ctx* ctx, unsigned long long* keys_in, unsigned lon
                           double* vals_out, size_t n, int end_bit, DBuf<char>& tmp, int begin_bit = 0);
 int sc_sort_pairs_u64_u32(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, unsigned* vals_in,
                           unsigned* vals_out, size_t n, int end_bit, DBuf<char>& tmp);
+int sc_sort_pairs_u32_u32(sc_ctx* ctx, unsigned* keys_in, unsigned* keys_out, unsigned* vals_in, unsigned* vals_out,
+                          size_t n, int end_bit, DBuf<char>& tmp);
 int sc_sort_keys_u64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, size_t n, int end_bit,
                      DBuf<char>& tmp);
 int sc_sum_f64(sc_ctx* ctx, const double* in, double* out, size_t n, DBuf<char>& tmp);

@@ -179,6 +179,85 @@ k_push_emit(PushSrc src, RowLists K, PushFilter f, const long long* __restrict__
     o += __popc(ball);
   }
 }
+// One source per archetype (the one-hot E_t of a Frank-Wolfe step): nothing to sum, so the triples only have to be grouped
+// by target cell.  Two cheaper-looking variants were measured at 1M cells and dropped: a 64-bit (cell, archetype) radix
+// sort of the ~10 M triples (0.6 ms in CUB alone) and a histogram + atomic-cursor scatter + per-row rank sort (1.1 ms: hub
+// cells of the kNN graph receive hundreds of entries per step, and returning atomics on one address serialise).
+// Work is split by ENTRY, not by source: rows of K range from a few dozen to tens of thousands of entries (hub cells of the
+// kNN graph), and a warp per source left the whole launch waiting for the longest row.  off = exclusive scan of the
+// sources' row lengths; thread e finds its source by binary search in `off` (k + 1 values, cache resident).
+__global__ void k_src_len(PushSrc src, RowLists K, int* __restrict__ len_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > src.m) return;
+  len_out[s] = (s < src.m) ? K.len[src.cell[s]] : 0;
+}
+__device__ __forceinline__ int push_find_source(const long long* __restrict__ off, int m, long long e) {
+  int lo = 0, hi = m;  // largest s with off[s] <= e
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= e) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+// 32-bit sort keys: the target cell (the sort is stable and the flattened entries are emitted source by source, so inside a
+// cell the entries stay in ascending-archetype order).  pos = null: every entry is kept (single GPU); otherwise
+// pos[e] = exclusive scan of the keep flags and only kept entries are written, compacted.
+__global__ void __launch_bounds__(256)
+k_push_flags(PushSrc src, RowLists K, PushFilter f, const long long* __restrict__ off, int* __restrict__ flags) {
+  const long long total = off[src.m];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e <= total; e += (long long)gridDim.x * blockDim.x) {
+    int keep = 0;
+    if (e < total) {
+      const int s = push_find_source(off, src.m, e);
+      keep = push_keep(f, K.key[K.ptr[src.cell[s]] + (e - off[s])]) ? 1 : 0;
+    }
+    flags[e] = keep;  // flags[total] = 0: the scan ends with the count
+  }
+}
+__global__ void __launch_bounds__(256)
+k_push_keys(PushSrc src, RowLists K, const long long* __restrict__ off, const int* __restrict__ flags,
+            const long long* __restrict__ pos, unsigned* __restrict__ keys, unsigned* __restrict__ idx,
+            int* __restrict__ flat_a, double* __restrict__ flat_v) {
+  const long long total = off[src.m];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    if (flags && !flags[e]) continue;
+    const int s = push_find_source(off, src.m, e);
+    const long long o = pos ? pos[e] : e;
+    const long long kp = K.ptr[src.cell[s]] + (e - off[s]);
+    keys[o] = (unsigned)K.key[kp];
+    idx[o] = (unsigned)o;
+    flat_a[o] = src.key ? src.key[s] : s;  // read here, coalesced along the row of K; the gather after the sort then
+    flat_v[o] = K.val[kp];                 // reads two compact, L2-resident arrays instead of the 9 GB of K
+  }
+}
+// sorted position j -> (archetype, value) of the emitted entry idx[j]
+__global__ void __launch_bounds__(256)
+k_push_gather(long long kept, const unsigned* __restrict__ idx, const int* __restrict__ flat_a,
+              const double* __restrict__ flat_v, int* __restrict__ z_key, double* __restrict__ z_val) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < kept; j += (long long)gridDim.x * blockDim.x) {
+    const unsigned o = idx[j];
+    z_key[j] = flat_a[o];
+    z_val[j] = flat_v[o];
+  }
+}
+__global__ void k_rows_from_keys32(int rows, long long total, const unsigned* __restrict__ keys, long long* __restrict__ ptr,
+                                   int* __restrict__ len) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > rows) return;
+  auto lower = [&](unsigned target) {
+    long long lo = 0, hi = total;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (keys[mid] < target) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  const long long lo = lower((unsigned)t);
+  ptr[t] = lo;
+  if (t < rows) len[t] = (int)(lower((unsigned)t + 1u) - lo);
+}
 // sorted triples -> row lists.  heads[e] = 1 where a new (cell, archetype) run starts.
 __global__ void k_run_heads(long long total, const unsigned long long* __restrict__ keys, long long* __restrict__ heads) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,10 +298,6 @@ __global__ void k_rows_from_ckeys(int rows, const long long* __restrict__ total_
   const long long lo = lower((unsigned long long)(unsigned)t << kbits);
   ptr[t] = lo;
   if (t < rows) len[t] = (int)(lower((unsigned long long)(unsigned)(t + 1) << kbits) - lo);
-}
-__global__ void k_unpack_low(long long total, const unsigned long long* __restrict__ keys, int kbits, int* __restrict__ out) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < total) out[e] = (int)(keys[e] & ((1ull << kbits) - 1ull));
 }
 // B slots -> push sources (archetype-major, slot order)
 __global__ void k_b_sources(int k, int S, const int* __restrict__ b_idx, const double* __restrict__ b_val,
@@ -762,13 +837,18 @@ struct UpdBArgs {
   const int* c_cell;
   const double* c_t2;
   RowLists KB;   // (K B)[cell, :] for the current B
-  RowLists T2c;  // (K A^T)[cell, :] sorted by archetype (dense-scan lookups)
+  RowLists T2c;  // (K A^T)[cell, :], first-occurrence order (dense-scan lookups)
   int* b_idx;
   double* b_val;
   int* b_cnt;
   int* trace;  // [T * k] or null
   int* amin;   // [k] or null: the cell chosen for every archetype at this step (feeds the incremental K B update)
   unsigned long long* evaluated;  // diagnostics: candidates whose exact gradient was computed
+  // round 0 seeds the pruning bound from the r0n largest-t2 candidates and - from the second Frank-Wolfe step on - from
+  // the cell the archetype chose at the previous step (prev, null at step 0), whose gradient is usually the minimum again
+  int r0n = 64;
+  const int* prev = nullptr;
+  int row_begin = 0, row_end = 0;
 };
 
 constexpr int UPB_CHUNK = 1024;  // candidates per CTA
@@ -818,6 +898,9 @@ __global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restric
 // warp keeps ~20 independent loads in flight instead of walking one cell through four dependent round trips (the first
 // version ran at 37 % warps active and 1.4 TB/s; it was latency bound, not bandwidth bound).  Lane l owns hubs l, l + 32,
 // ...; R = nh_pad / 32.  Per (cell, hub) the arithmetic and its order are unchanged.
+// (A version that staged the list headers and entries of a CTA's 256 cells in shared memory and kept HH / t2 in the
+// locality order was measured and dropped: 1.5 ms against 0.94 ms for this one at 1M cells - its warps walk separate
+// 32-cell blocks, the L1 hit rate of the t1 gathers fell from 70 % to 29 %, and the stages serialise behind barriers.)
 template <int R, int HUB_UNROLL>
 __global__ void __launch_bounds__(256, 2) k_updateB_hub(int row_begin, int row_end, int nh_pad,
                                                         const int* __restrict__ perm, RowLists KB,
@@ -1037,7 +1120,7 @@ __global__ void k_row_max(int r0, int r1, RowLists L, double* __restrict__ mv, i
 // bound exceeds it can neither be the argmin nor tie with it and is skipped without reading its K B row.  This is what
 // keeps long candidate lists affordable.  round 0 = first UPB_R0 candidates of every archetype,
 // round 1 = everything else.
-constexpr int UPB_R0 = 64;  // candidates evaluated unconditionally to seed the bound
+constexpr int UPB_R0 = 64;  // candidates evaluated unconditionally to seed the bound at step 0 (UpdBArgs::r0n later)
 __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, const long long* __restrict__ chunk_ptr,
                                                       const int* __restrict__ chunk_arch,
                                                       const double* __restrict__ cmax_v, const int* __restrict__ cmax_l,
@@ -1059,8 +1142,8 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   const long long c0 = g.c_ptr[a] + (long long)chunk * UPB_CHUNK;
   const int nc = (int)min((long long)UPB_CHUNK, g.c_ptr[a + 1] - c0);
   const double bound = (round == 0) ? FW_INF : bound_v[a];
-  const int e_begin = (round == 1 && chunk == 0) ? UPB_R0 : 0;
-  const int e_end = (round == 0) ? min(nc, UPB_R0) : nc;
+  const int e_begin = (round == 1 && chunk == 0) ? g.r0n : 0;
+  const int e_end = (round == 0) ? min(nc, g.r0n) : nc;
   // phase 1: cheap bound tests, survivors compacted into shared memory
   __shared__ int q_cell[UPB_CHUNK];
   __shared__ double q_t2[UPB_CHUNK];
@@ -1094,6 +1177,20 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
     }
   }
   __syncthreads();
+  if (round == 0 && g.prev) {  // the previous winner, if it is one of this rank's candidates of archetype a
+    const int pc = g.prev[a];
+    if (pc >= g.row_begin && pc < g.row_end) {
+      const long long tp = g.T2c.ptr[pc];
+      const int tl = g.T2c.len[pc];
+      for (int x = threadIdx.x; x < tl; x += 256)
+        if (g.T2c.key[tp + x] == a) {  // at most one entry matches
+          const int pos = atomicAdd(&q_n, 1);
+          q_cell[pos] = pc;
+          q_t2[pos] = g.T2c.val[tp + x];
+        }
+    }
+    __syncthreads();
+  }
   const int nq = q_n;
   if (threadIdx.x == 0 && g.evaluated) atomicAdd(g.evaluated, (unsigned long long)nq);
   // phase 2: exact gradient of the survivors.  A chunk keeps a few dozen of its 1024 candidates, so one survivor per
@@ -1192,13 +1289,8 @@ __global__ void __launch_bounds__(256) k_updateB_local(UpdBArgs g, int row_begin
       if (i < row_end) {
         const long long tp = g.T2c.ptr[i];
         const int tl = g.T2c.len[i];
-        int lo = 0, hi = tl;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (g.T2c.key[tp + mid] < a) lo = mid + 1;
-          else hi = mid;
-        }
-        const bool is_cand = lo < tl && g.T2c.key[tp + lo] == a;
+        bool is_cand = false;  // rows of t2 are in first-occurrence order: linear scan (this path is rare)
+        for (int x = 0; x < tl && !is_cand; ++x) is_cand = g.T2c.key[tp + x] == a;
         if (!is_cand) {
           const long long p = g.KB.ptr[i];
           const int L = g.KB.len[i];
@@ -1323,13 +1415,11 @@ __global__ void k_merge_len(int n, const int* __restrict__ la, const int* __rest
 
 // New[i,:] = c_old * Old[i,:] (+) c_new * D[i,:] for rows [r0, r1), one warp per row.  Entries of Old keep their order,
 // keys that are new to the row are appended in D's order (both orders are fixed => bitwise reproducible).
-__global__ void __launch_bounds__(256)
-k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict__ new_ptr, int* __restrict__ new_len,
-           int* __restrict__ new_key, double* __restrict__ new_val, double c_old, double c_new,
-           double* __restrict__ max_v, int* __restrict__ max_l) {
+__device__ __forceinline__ void kb_merge_row(int i, const RowLists& Old, const RowLists& D,
+                                             const long long* __restrict__ new_ptr, int* __restrict__ new_len,
+                                             int* __restrict__ new_key, double* __restrict__ new_val, double c_old,
+                                             double c_new, double* __restrict__ max_v, int* __restrict__ max_l) {
   const int lane = threadIdx.x & 31;
-  const int i = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (i >= r1) return;
   const int lo = Old.len[i], ld = D.len[i];
   const long long po = Old.ptr[i], pd = D.ptr[i], pn = new_ptr[i];
   // the row's largest entry (value, then smaller key) rides along: it feeds the second pruning bound of k_updateB_eval
@@ -1439,6 +1529,146 @@ k_kb_merge(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict
   }
   if (lane == 0) new_len[i] = lo + napp;
   finish_max();
+}
+// generic kernel: the listed rows (handed over by the staged kernel), one warp per row
+__global__ void __launch_bounds__(256)
+k_kb_merge(RowLists Old, RowLists D, const long long* __restrict__ new_ptr, int* __restrict__ new_len,
+           int* __restrict__ new_key, double* __restrict__ new_val, double c_old, double c_new,
+           double* __restrict__ max_v, int* __restrict__ max_l, const int* __restrict__ list,
+           const int* __restrict__ list_count) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int count = *list_count;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps)
+    kb_merge_row(list[w], Old, D, new_ptr, new_len, new_key, new_val, c_old, c_new, max_v, max_l);
+}
+
+// Staged version of the same merge (same arithmetic, same output order).  The warp-per-row kernel above spent ~670 warp
+// instructions per row broadcasting every delta entry to every batch of old entries with shuffles and votes (ncu: 60 % SM
+// throughput, 1.6 GB of traffic in 0.98 ms).  Here a CTA stages the delta rows of its 64 cells in shared memory; a lane
+// that holds an old entry compares it against the staged keys with broadcast shared-memory reads, marks matches in a
+// shared flag array, and the unmatched delta entries are appended in their (canonical) order.
+constexpr int KBM_ROWS = 64;     // rows per CTA (8 per warp)
+constexpr int KBM_ECAP = 2048;   // staged delta entries per CTA
+__global__ void __launch_bounds__(256)
+k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __restrict__ new_ptr,
+                  int* __restrict__ new_len, int* __restrict__ new_key, double* __restrict__ new_val, double c_old,
+                  double c_new, double* __restrict__ max_v, int* __restrict__ max_l, int* __restrict__ slow_list,
+                  int* __restrict__ slow_count) {
+  __shared__ double s_dv[KBM_ECAP];
+  __shared__ int s_dk[KBM_ECAP];
+  __shared__ unsigned char s_match[KBM_ECAP];
+  __shared__ long long s_pd[KBM_ROWS];
+  __shared__ int s_ld[KBM_ROWS], s_doff[KBM_ROWS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = r0 + blockIdx.x * KBM_ROWS;
+  const int nrow = min(KBM_ROWS, r1 - row0);
+  if (threadIdx.x < KBM_ROWS) {
+    int ld = 0;
+    if ((int)threadIdx.x < nrow) {
+      ld = D.len[row0 + threadIdx.x];
+      s_pd[threadIdx.x] = D.ptr[row0 + threadIdx.x];
+    }
+    s_ld[threadIdx.x] = ld;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of 64 lengths by one warp
+    const int a = s_ld[lane], b = s_ld[lane + 32];
+    int ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int va = __shfl_up_sync(0xffffffffu, ia, d), vb = __shfl_up_sync(0xffffffffu, ib, d);
+      if (lane >= d) {
+        ia += va;
+        ib += vb;
+      }
+    }
+    const int tota = __shfl_sync(0xffffffffu, ia, 31);
+    s_doff[lane] = ia - a;
+    s_doff[lane + 32] = tota + ib - b;
+    if (lane == 31) s_doff[64] = tota + ib;
+  }
+  for (int t = threadIdx.x; t < KBM_ECAP; t += 256) s_match[t] = 0;
+  __syncthreads();
+  for (int j = 0; j < KBM_ROWS / 8; ++j) {  // stage the delta rows: warp w takes rows w, w + 8, ...
+    const int rr = warp + 8 * j;
+    const int ld = s_ld[rr], doff = s_doff[rr];
+    if (doff + ld > KBM_ECAP) continue;
+    const long long pd = s_pd[rr];
+    for (int x = lane; x < ld; x += 32) {
+      s_dk[doff + x] = D.key[pd + x];
+      s_dv[doff + x] = D.val[pd + x];
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < KBM_ROWS / 8; ++j) {
+    const int rr = warp + 8 * j;
+    if (rr >= nrow) break;
+    const int i = row0 + rr;
+    const int ld = s_ld[rr], doff = s_doff[rr];
+    if (doff + ld > KBM_ECAP) {  // does not fit the staging area: the generic kernel takes this row
+      if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = i;
+      continue;
+    }
+    const int lo = Old.len[i];
+    const long long po = Old.ptr[i], pn = new_ptr[i];
+    double bv = -1.0;
+    int bk = 0x7fffffff;
+    for (int ob = 0; ob < lo; ob += 32) {
+      const bool ov = ob + lane < lo;
+      int ok = -2;
+      double val = 0.0;
+      if (ov) {
+        ok = Old.key[po + ob + lane];
+        val = __dmul_rn(c_old, Old.val[po + ob + lane]);
+      }
+      for (int d = 0; d < ld; ++d) {
+        if (ok == s_dk[doff + d]) {
+          val = __dadd_rn(val, __dmul_rn(c_new, s_dv[doff + d]));
+          s_match[doff + d] = 1;
+        }
+      }
+      if (ov) {
+        new_key[pn + ob + lane] = ok;
+        new_val[pn + ob + lane] = val;
+        if (val > bv || (val == bv && ok < bk)) {
+          bv = val;
+          bk = ok;
+        }
+      }
+    }
+    __syncwarp();
+    int napp = 0;
+    for (int db = 0; db < ld; db += 32) {
+      const bool app = db + lane < ld && !s_match[doff + db + lane];
+      const unsigned ball = __ballot_sync(0xffffffffu, app);
+      if (app) {
+        const int pos = lo + napp + __popc(ball & ((1u << lane) - 1u));
+        const int dk = s_dk[doff + db + lane];
+        const double nvv = __dmul_rn(c_new, s_dv[doff + db + lane]);
+        new_key[pn + pos] = dk;
+        new_val[pn + pos] = nvv;
+        if (nvv > bv || (nvv == bv && dk < bk)) {
+          bv = nvv;
+          bk = dk;
+        }
+      }
+      napp += __popc(ball);
+    }
+    if (lane == 0) new_len[i] = lo + napp;
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+      const double ov2 = __shfl_xor_sync(0xffffffffu, bv, dd);
+      const int ok2 = __shfl_xor_sync(0xffffffffu, bk, dd);
+      if (ov2 > bv || (ov2 == bv && ok2 < bk)) {
+        bv = ov2;
+        bk = ok2;
+      }
+    }
+    if (lane == 0) {
+      max_v[i] = bv > 0.0 ? bv : 0.0;
+      max_l[i] = bv > 0.0 ? bk : 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ RSS, labels
@@ -1569,6 +1799,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
   resum_A = std::getenv("SC_FIT_RESUM_A") != nullptr;
   if (const char* e = std::getenv("SC_HUB_MAX")) hub_cap = std::max(0, std::min(HUB_MAX, atoi(e)));
+  if (const char* e = std::getenv("SC_R0_SEED")) r0_seed = std::max(0, std::min(UPB_R0, atoi(e)));
   n = n_;
   row_begin = 0;
   row_end = n_;
@@ -1728,11 +1959,56 @@ int sc_fit::push_product(const PushSrc& src, const PushFilter& f, bool has_dups,
   while ((1ll << kbits) < k) kbits++;
   while ((1ll << nbits) < n) nbits++;
   RowLists Kv = Kl.view();
-  SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
-  SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
   SC_TRY(Z.ptr.ensure(ctx, (size_t)n + 1));
   SC_TRY(Z.len.ensure(ctx, (size_t)n + 1));
   Z.rows = n;
+  if (!has_dups) {
+    // flatten (source, entry) -> 32-bit radix sort by target cell -> gather; insensitive to the skew of the rows of K
+    SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
+    SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
+    SC_LAUNCH(ctx, k_src_len, (m + 256) / 256, 256, 0, src, Kv, ps_cnt.p);
+    SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
+    long long total = 0, kept = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total >= (1ll << 32)) SC_FAIL(ctx, SC_ERR_CAPACITY, "push product: more than 2^32 entries in one step");
+    const unsigned fgrid = 148 * 16;  // grid-stride over the flattened entries
+    const bool filtered = !(f.r0 == 0 && f.r1 == n);
+    const int* flags = nullptr;
+    const long long* pos = nullptr;
+    kept = total;
+    if (filtered && total > 0) {
+      SC_TRY(push_flags.ensure(ctx, (size_t)total + 1));
+      SC_TRY(run_pos.ensure(ctx, (size_t)total + 1));
+      SC_LAUNCH(ctx, k_push_flags, fgrid, 256, 0, src, Kv, f, ps_off.p, push_flags.p);
+      SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, push_flags.p, run_pos.p, (size_t)total + 1, tmp));
+      SC_CUDA(ctx, cudaMemcpyAsync(&kept, run_pos.p + total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      flags = push_flags.p;
+      pos = run_pos.p;
+    }
+    last_push_total = kept;
+    SC_TRY(Z.key.ensure(ctx, (size_t)kept + 1));
+    SC_TRY(Z.val.ensure(ctx, (size_t)kept + 1));
+    if (kept == 0) {
+      SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
+      SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+      return SC_OK;
+    }
+    SC_TRY(pk32_in.ensure(ctx, (size_t)kept + 1));
+    SC_TRY(pk32_out.ensure(ctx, (size_t)kept + 1));
+    SC_TRY(pi32_in.ensure(ctx, (size_t)kept + 1));
+    SC_TRY(pi32_out.ensure(ctx, (size_t)kept + 1));
+    SC_TRY(flat_a.ensure(ctx, (size_t)kept + 1));  // flat (archetype, value) of the emitted entries
+    SC_TRY(pv_in.ensure(ctx, (size_t)kept + 1));
+    SC_LAUNCH(ctx, k_push_keys, fgrid, 256, 0, src, Kv, ps_off.p, flags, pos, pk32_in.p, pi32_in.p, flat_a.p, pv_in.p);
+    SC_TRY(sc_sort_pairs_u32_u32(ctx, pk32_in.p, pk32_out.p, pi32_in.p, pi32_out.p, (size_t)kept, nbits, tmp));
+    SC_LAUNCH(ctx, k_push_gather, fgrid, 256, 0, kept, pi32_out.p, flat_a.p, pv_in.p, Z.key.p, Z.val.p);
+    SC_LAUNCH(ctx, k_rows_from_keys32, (n + 256) / 256, 256, 0, n, kept, pk32_out.p, Z.ptr.p, Z.len.p);
+    return SC_OK;
+  }
+  SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
+  SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
   const unsigned wgrid = (unsigned)((((size_t)m + 1) * 32 + 255) / 256);
   SC_LAUNCH(ctx, k_push_count, wgrid, 256, 0, src, Kv, f, ps_cnt.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
@@ -1752,14 +2028,6 @@ int sc_fit::push_product(const PushSrc& src, const PushFilter& f, bool has_dups,
   }
   SC_LAUNCH(ctx, k_push_emit, wgrid, 256, 0, src, Kv, f, ps_off.p, kbits, pk_keys_in.p, pv_in.p);
   const unsigned egrid = (unsigned)((total + 256) / 256);
-  if (!has_dups) {
-    // stable sort on the cell bits only: inside a cell the emission order (ascending archetype) is kept
-    SC_TRY(sc_sort_pairs_u64_f64(ctx, pk_keys_in.p, pk_keys_out.p, pv_in.p, Z.val.p, (size_t)total, kbits + nbits, tmp,
-                                 kbits));
-    SC_LAUNCH(ctx, k_unpack_low, egrid, 256, 0, total, pk_keys_out.p, kbits, Z.key.p);
-    SC_LAUNCH(ctx, k_rows_from_ckeys, (n + 256) / 256, 256, 0, n, ps_off.p + m, pk_keys_out.p, kbits, Z.ptr.p, Z.len.p);
-    return SC_OK;
-  }
   SC_TRY(pv_out.ensure(ctx, (size_t)total + 1));
   SC_TRY(run_heads.ensure(ctx, (size_t)total + 1));
   SC_TRY(run_pos.ensure(ctx, (size_t)total + 1));
@@ -1843,9 +2111,15 @@ int sc_fit::advance_KB(int t) {
     SC_TRY(KB2.val.ensure(ctx, (size_t)total + 1));
     KB2.rows = n;
     const int rows = row_end - row_begin;
-    if (rows > 0)
-      SC_LAUNCH(ctx, k_kb_merge, (unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, row_begin, row_end, KB.view(),
-                DKB.view(), KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p, 1.0 - gamma, gamma, cmax_v.p, cmax_l.p);
+    if (rows > 0) {
+      SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
+      SC_LAUNCH(ctx, k_kb_merge_staged, (rows + KBM_ROWS - 1) / KBM_ROWS, 256, 0, row_begin, row_end, KB.view(), DKB.view(),
+                KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p, 1.0 - gamma, gamma, cmax_v.p, cmax_l.p, slow_list.p,
+                slow_cnt.p);
+      // rows whose CTA overflowed the staging area (cells next to very many chosen cells): generic kernel, a few warps
+      SC_LAUNCH(ctx, k_kb_merge, 148, 256, 0, KB.view(), DKB.view(), KB2.ptr.p, KB2.len.p, KB2.key.p, KB2.val.p,
+                1.0 - gamma, gamma, cmax_v.p, cmax_l.p, slow_list.p, slow_cnt.p);
+    }
     swap_lists(KB, KB2);
   }
   pstop(P_SPGEMM_KB);
@@ -2020,8 +2294,10 @@ int sc_fit::update_B_begin() {
   // ---- t2 = K A^T as per-cell rows, then as per-archetype candidate lists
   pstart();
   RowLists Al{slot_ptr_n.p, a_cnt[cur].p, a_idx[cur].p, a_val[cur].p};
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp));
-  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MA.view(), k, T2c, sp));  // candidates: this rank's cells only
+  // rows in first-occurrence order (no compaction, no sort): the values do not depend on the order inside a row of the
+  // right-hand side (a key occurs once per row), and the candidate lists are ordered by the radix sort below
+  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp, false));
+  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MA.view(), k, T2c, sp, false));  // candidates: this rank's cells only
   pstop(P_T2ROWS);
   pstart();
   {
@@ -2147,6 +2423,10 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   g.trace = nullptr;
   g.amin = nullptr;
   g.evaluated = eval_cnt.p;
+  g.row_begin = row_begin;
+  g.row_end = row_end;
+  g.prev = (t > 0 && r0_seed > 0) ? amin_cur.p : nullptr;
+  g.r0n = (t > 0 && r0_seed > 0) ? r0_seed : UPB_R0;
   const long long nchunks = nchunks_cur;
   pstart();
   if ((int)ev_a.size() <= t) {
@@ -2188,8 +2468,8 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     }
     SC_CUDA(ctx, cudaEventRecord(ev_h0[t], ctx->stream));
 #define SC_HUB_LAUNCH(RR)                                                                                              \
-  SC_LAUNCH(ctx, (k_updateB_hub<RR, (RR <= 2 ? 4 : 2)>), nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, hub_rows, T1H.p, T2H.p, HH.p, \
-            inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p)
+  SC_LAUNCH(ctx, (k_updateB_hub<RR, (RR <= 2 ? 4 : 2)>), nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, hub_rows, \
+            T1H.p, T2H.p, HH.p, inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p)
     if (nctas > 0) switch (n_hub_pad / 32) {
       case 1: SC_HUB_LAUNCH(1); break;
       case 2: SC_HUB_LAUNCH(2); break;

@@ -39,7 +39,8 @@ struct sc_fit {
   DBuf<double> src_w, pv_in, pv_out;
   DBuf<long long> ps_off, run_heads, run_pos;
   DBuf<unsigned long long> pk_keys_in, pk_keys_out, ckeys;
-  DBuf<unsigned> supp_bits;
+  DBuf<unsigned> supp_bits, pk32_in, pk32_out, pi32_in, pi32_out;
+  DBuf<int> push_flags, flat_a;
   // compressed B
   DBuf<int> b_idx, b_cnt;
   DBuf<double> b_val;
@@ -48,6 +49,7 @@ struct sc_fit {
   // incremental K B inside one _updateB call: chosen cells of the last step, K E, second K B buffer
   DBuf<int> amin_cur;
   RowListsBuf DKB, KB2;
+  int r0_seed = 16;  // round 0 of the gradient kernel after step 0: previous winner + this many largest-t2 candidates (0: 64, no seed)
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step

@@ -451,6 +451,90 @@ k_spgemm_big(int nbig, const int* __restrict__ big_list, int key_space, const in
   }
 }
 
+// First-occurrence callers (order inside a row is irrelevant to them) get a cheaper big-row kernel: one CTA per row, an
+// open-addressing table of HCAP slots in shared memory instead of a dense accumulator over the key space (K = M M^T has
+// key space n = 10^6 and ~10 % of its rows exceed the per-warp table: the dense kernel spent 1.2 s zeroing and scanning
+// 8 MB per row).  The rows of X are applied one after the other (a key occurs once per row of X, so the adds of one pass
+// hit distinct slots): per key the accumulation order is again ascending position in the row of S => fixed values.
+// Which slot a key lands in depends on the race between inserting threads, so the ORDER of the output row is not
+// reproducible; rows that do not fit (more than 7/8 HCAP distinct keys) are handed on to the dense kernel.
+constexpr int HCAP = 8192;
+__global__ void __launch_bounds__(BIG_THREADS)
+k_spgemm_big_hash(int nbig, const int* __restrict__ big_list, const int* __restrict__ s_ptr,
+                  const int* __restrict__ s_col, const double* __restrict__ s_val, RowLists X,
+                  const long long* __restrict__ z_ptr, int* __restrict__ z_len, int* __restrict__ z_key,
+                  double* __restrict__ z_val, int* __restrict__ flags, int* __restrict__ dense_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tvals = reinterpret_cast<double*>(smem_raw);
+  int* tkeys = reinterpret_cast<int*>(smem_raw + (size_t)HCAP * sizeof(double));
+  __shared__ int s_count, s_over, s_out;
+  const int tid = threadIdx.x;
+  constexpr int LIMIT = HCAP - (HCAP >> 3);
+  for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
+    const int i = big_list[w];
+    for (int t = tid; t < HCAP; t += BIG_THREADS) {
+      tkeys[t] = -1;
+      tvals[t] = 0.0;
+    }
+    if (tid == 0) {
+      s_count = 0;
+      s_over = 0;
+      s_out = 0;
+    }
+    __syncthreads();
+    for (int p = s_ptr[i]; p < s_ptr[i + 1]; ++p) {
+      const int q = s_col[p];
+      const double m = s_val[p];
+      const long long xp = X.ptr[q];
+      const int xl = X.len[q];
+      for (int x = tid; x < xl; x += BIG_THREADS) {
+        const int key = X.key[xp + x];
+        const double c = __dmul_rn(m, X.val[xp + x]);
+        int sl = hash_key(key) & (HCAP - 1);
+        bool placed = false;
+        for (int probe = 0; probe < HCAP; ++probe) {
+          const int prev = atomicCAS(&tkeys[sl], -1, key);
+          if (prev == -1) {
+            if (atomicAdd(&s_count, 1) >= LIMIT) s_over = 1;
+            placed = true;
+            break;
+          }
+          if (prev == key) {
+            placed = true;
+            break;
+          }
+          sl = (sl + 1) & (HCAP - 1);
+        }
+        if (placed) tvals[sl] = __dadd_rn(tvals[sl], c);
+        else s_over = 1;
+      }
+      __syncthreads();
+      if (s_over) break;
+    }
+    __syncthreads();
+    if (s_over) {
+      if (tid == 0) {
+        dense_list[atomicAdd(&flags[1], 1)] = i;
+        z_len[i] = 0;
+      }
+      __syncthreads();
+      continue;
+    }
+    const long long zp = z_ptr[i];
+    for (int t = tid; t < HCAP; t += BIG_THREADS) {
+      const int key = tkeys[t];
+      if (key != -1) {
+        const int pos = atomicAdd(&s_out, 1);
+        z_key[zp + pos] = key;
+        z_val[zp + pos] = tvals[t];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) z_len[i] = s_out;
+    __syncthreads();
+  }
+}
+
 int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, const RowLists& X, int key_space,
                    RowListsBuf& Z, SpgemmScratch& sc, bool sorted, bool wide) {
   constexpr int CAP = 512, WARPS = 8;
@@ -502,10 +586,21 @@ int sc_spgemm_rows(sc_ctx* ctx, const CsrView& S, int row_begin, int row_end, co
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   sc.last_big_rows = nbig;
   sc.total_big_rows += nbig;
+  const int* dense_rows = sc.big_list.p;
+  if (nbig > 0 && !sorted) {
+    SC_TRY(sc.dense_list.ensure(ctx, (size_t)n));
+    const size_t hsmem = (size_t)HCAP * (sizeof(double) + sizeof(int));
+    SC_CUDA(ctx, cudaFuncSetAttribute(k_spgemm_big_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    SC_LAUNCH(ctx, k_spgemm_big_hash, std::min(nbig, 148 * 2), BIG_THREADS, hsmem, nbig, sc.big_list.p, S.indptr, S.indices,
+              S.data, X, Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.flags.p, sc.dense_list.p);
+    SC_CUDA(ctx, cudaMemcpyAsync(&nbig, sc.flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dense_rows = sc.dense_list.p;
+  }
   if (nbig > 0) {
     const int bgrid = std::min(nbig, 148 * 2);
     SC_TRY(sc.big_acc.ensure(ctx, (size_t)bgrid * key_space));
-    SC_LAUNCH(ctx, k_spgemm_big, bgrid, BIG_THREADS, 0, nbig, sc.big_list.p, key_space, S.indptr, S.indices, S.data, X,
+    SC_LAUNCH(ctx, k_spgemm_big, bgrid, BIG_THREADS, 0, nbig, dense_rows, key_space, S.indptr, S.indices, S.data, X,
               Z.ptr.p, Z.len.p, Z.key.p, Z.val.p, sc.big_acc.p);
   }
   return SC_OK;

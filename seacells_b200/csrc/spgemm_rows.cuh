@@ -3,7 +3,7 @@
 
 struct SpgemmScratch {
   DBuf<long long> ub;
-  DBuf<int> flags, big_list;
+  DBuf<int> flags, big_list, dense_list;
   DBuf<double> big_acc;
   DBuf<char> tmp;
   int last_big_rows = 0;

@@ -50,6 +50,18 @@ int sc_sort_pairs_u64_u32(sc_ctx* ctx, unsigned long long* keys_in, unsigned lon
   return SC_OK;
 }
 
+int sc_sort_pairs_u32_u32(sc_ctx* ctx, unsigned* keys_in, unsigned* keys_out, unsigned* vals_in, unsigned* vals_out,
+                          size_t n, int end_bit, DBuf<char>& tmp) {
+  size_t bytes = 0;
+  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n, 0,
+                                               end_bit, ctx->stream));
+  SC_TRY(tmp.ensure(ctx, bytes));
+  SC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_in, keys_out, vals_in, vals_out, (long long)n, 0,
+                                               end_bit, ctx->stream));
+  ctx->launches += 1;
+  return SC_OK;
+}
+
 int sc_sort_keys_u64(sc_ctx* ctx, unsigned long long* keys_in, unsigned long long* keys_out, size_t n, int end_bit,
                      DBuf<char>& tmp) {
   size_t bytes = 0;

@@ -605,7 +605,9 @@ int sc_fit_stats(sc_fit* fit, long long* out4) {
   out4[8] = fit->hub_steps;
   out4[9] = (long long)(fit->hub_ms_total * 1e6);
   out4[10] = fit->hub_launches_counted ? (long long)(fit->hub_bytes_total / (double)fit->hub_launches_counted) : 0;
-  for (int i = 11; i < 16; ++i) out4[i] = 0;
+  out4[11] = fit->last_pruned_chunks;
+  out4[12] = fit->last_chunk_launches;
+  for (int i = 13; i < 16; ++i) out4[i] = 0;
   return SC_OK;
 }
 int sc_fit_profile(sc_fit* fit, double* out16) {

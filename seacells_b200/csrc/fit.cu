@@ -117,75 +117,20 @@ __global__ void k_lists_from_sorted(int rows, long long total, const unsigned lo
 // w K[c, i] to (cell i, archetype a) for the stored entries of row c of K, the triples are grouped by a stable radix
 // sort on (cell, archetype) and runs of equal (cell, archetype) are summed in emission order (ascending archetype, then
 // slot) - a fixed order, so the result is bitwise reproducible and independent of how the cells are sharded.
-// The work is proportional to the number of sources x ~400, not to n x (row work): 5 M triples for one step's K E_t at
+// The work is proportional to the number of sources x ~770, not to n x (row work): 10 M triples for one step's K E_t at
 // 1M cells, where the row-wise two-stage product M (M E_t) launched over all n rows cost 1.5 ms per step.
+// A rank of a sharded job forms only the COLUMNS of K that belong to its own slab of cells, K[:, slab] = M M[slab, :]^T:
+// a 1/world share of the memory and of the build, and every entry of a row it stores is one of its own target cells, so
+// the products need no filtering and no pass over other ranks' entries.
 struct PushSrc {
   int m;                  // sources
   const int* cell;        // [m] source cell c
   const int* key;         // [m] archetype a, or null: a = source index
   const double* w;        // [m] weight, or null: 1.0
 };
-// which target cells are kept: this rank's slab [r0, r1) plus cells whose bit is set in `extra` (may be null)
-struct PushFilter {
-  int r0, r1;
-  const unsigned* extra;
-};
-__device__ __forceinline__ bool push_keep(const PushFilter& f, int i) {
-  return (i >= f.r0 && i < f.r1) || (f.extra && ((f.extra[i >> 5] >> (i & 31)) & 1u));
-}
-__global__ void __launch_bounds__(256) k_push_count(PushSrc src, RowLists K, PushFilter f, int* __restrict__ cnt) {
-  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (s > src.m) return;
-  if (s == src.m) {
-    if (lane == 0) cnt[s] = 0;  // so that the exclusive scan over m + 1 values ends with the total
-    return;
-  }
-  const int c = src.cell[s];
-  const long long p = K.ptr[c];
-  const int L = K.len[c];
-  int tot = 0;
-  for (int x0 = 0; x0 < L; x0 += 32) {
-    const bool keep = (x0 + lane < L) && push_keep(f, K.key[p + x0 + lane]);
-    tot += __popc(__ballot_sync(0xffffffffu, keep));
-  }
-  if (lane == 0) cnt[s] = tot;
-}
-__global__ void __launch_bounds__(256)
-k_push_emit(PushSrc src, RowLists K, PushFilter f, const long long* __restrict__ off, int kbits,
-            unsigned long long* __restrict__ keys, double* __restrict__ vals) {
-  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (s >= src.m) return;
-  const int c = src.cell[s];
-  const unsigned long long a = (unsigned long long)(unsigned)(src.key ? src.key[s] : s);
-  const bool weighted = src.w != nullptr;
-  const double w = weighted ? src.w[s] : 1.0;
-  const long long p = K.ptr[c];
-  const int L = K.len[c];
-  long long o = off[s];
-  for (int x0 = 0; x0 < L; x0 += 32) {
-    int i = 0;
-    bool keep = false;
-    if (x0 + lane < L) {
-      i = K.key[p + x0 + lane];
-      keep = push_keep(f, i);
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const long long pos = o + __popc(ball & ((1u << lane) - 1u));
-      keys[pos] = ((unsigned long long)(unsigned)i << kbits) | a;
-      const double kv = K.val[p + x0 + lane];
-      vals[pos] = weighted ? __dmul_rn(w, kv) : kv;
-    }
-    o += __popc(ball);
-  }
-}
-// One source per archetype (the one-hot E_t of a Frank-Wolfe step): nothing to sum, so the triples only have to be grouped
-// by target cell.  Two cheaper-looking variants were measured at 1M cells and dropped: a 64-bit (cell, archetype) radix
-// sort of the ~10 M triples (0.6 ms in CUB alone) and a histogram + atomic-cursor scatter + per-row rank sort (1.1 ms: hub
-// cells of the kNN graph receive hundreds of entries per step, and returning atomics on one address serialise).
 // Work is split by ENTRY, not by source: rows of K range from a few dozen to tens of thousands of entries (hub cells of the
 // kNN graph), and a warp per source left the whole launch waiting for the longest row.  off = exclusive scan of the
-// sources' row lengths; thread e finds its source by binary search in `off` (k + 1 values, cache resident).
+// sources' row lengths; thread e finds its source by binary search in `off` (m + 1 values, cache resident).
 __global__ void k_src_len(PushSrc src, RowLists K, int* __restrict__ len_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > src.m) return;
@@ -200,35 +145,36 @@ __device__ __forceinline__ int push_find_source(const long long* __restrict__ of
   }
   return lo;
 }
-// 32-bit sort keys: the target cell (the sort is stable and the flattened entries are emitted source by source, so inside a
-// cell the entries stay in ascending-archetype order).  pos = null: every entry is kept (single GPU); otherwise
-// pos[e] = exclusive scan of the keep flags and only kept entries are written, compacted.
+// K B (several sources may share (cell, archetype)): 64-bit keys (cell << kbits | archetype), values w K[c, i]
 __global__ void __launch_bounds__(256)
-k_push_flags(PushSrc src, RowLists K, PushFilter f, const long long* __restrict__ off, int* __restrict__ flags) {
-  const long long total = off[src.m];
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e <= total; e += (long long)gridDim.x * blockDim.x) {
-    int keep = 0;
-    if (e < total) {
-      const int s = push_find_source(off, src.m, e);
-      keep = push_keep(f, K.key[K.ptr[src.cell[s]] + (e - off[s])]) ? 1 : 0;
-    }
-    flags[e] = keep;  // flags[total] = 0: the scan ends with the count
-  }
-}
-__global__ void __launch_bounds__(256)
-k_push_keys(PushSrc src, RowLists K, const long long* __restrict__ off, const int* __restrict__ flags,
-            const long long* __restrict__ pos, unsigned* __restrict__ keys, unsigned* __restrict__ idx,
-            int* __restrict__ flat_a, double* __restrict__ flat_v) {
+k_push_emit(PushSrc src, RowLists K, const long long* __restrict__ off, int kbits, unsigned long long* __restrict__ keys,
+            double* __restrict__ vals) {
   const long long total = off[src.m];
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    if (flags && !flags[e]) continue;
     const int s = push_find_source(off, src.m, e);
-    const long long o = pos ? pos[e] : e;
     const long long kp = K.ptr[src.cell[s]] + (e - off[s]);
-    keys[o] = (unsigned)K.key[kp];
-    idx[o] = (unsigned)o;
-    flat_a[o] = src.key ? src.key[s] : s;  // read here, coalesced along the row of K; the gather after the sort then
-    flat_v[o] = K.val[kp];                 // reads two compact, L2-resident arrays instead of the 9 GB of K
+    const unsigned long long a = (unsigned long long)(unsigned)(src.key ? src.key[s] : s);
+    keys[e] = ((unsigned long long)(unsigned)K.key[kp] << kbits) | a;
+    vals[e] = src.w ? __dmul_rn(src.w[s], K.val[kp]) : K.val[kp];
+  }
+}
+// One source per archetype (the one-hot E_t of a Frank-Wolfe step): nothing to sum, so the triples only have to be grouped
+// by target cell: 32-bit sort keys (the cell; the sort is stable and the flattened entries are emitted source by source,
+// so inside a cell they stay in ascending-archetype order) with the entry index as payload.  Two cheaper-looking
+// variants were measured at 1M cells and dropped: a 64-bit (cell, archetype) radix sort of the ~10 M triples (0.6 ms in
+// CUB alone) and a histogram + atomic-cursor scatter + per-row rank sort (1.1 ms: hub cells of the kNN graph receive
+// hundreds of entries per step, and returning atomics on one address serialise).
+__global__ void __launch_bounds__(256)
+k_push_keys(PushSrc src, RowLists K, const long long* __restrict__ off, unsigned* __restrict__ keys,
+            unsigned* __restrict__ idx, int* __restrict__ flat_a, double* __restrict__ flat_v) {
+  const long long total = off[src.m];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int s = push_find_source(off, src.m, e);
+    const long long kp = K.ptr[src.cell[s]] + (e - off[s]);
+    keys[e] = (unsigned)K.key[kp];
+    idx[e] = (unsigned)e;
+    flat_a[e] = src.key ? src.key[s] : s;  // read here, coalesced along the row of K; the gather after the sort then
+    flat_v[e] = K.val[kp];                 // reads two compact, L2-resident arrays instead of the 9 GB of K
   }
 }
 // sorted position j -> (archetype, value) of the emitted entry idx[j]
@@ -241,9 +187,9 @@ k_push_gather(long long kept, const unsigned* __restrict__ idx, const int* __res
     z_val[j] = flat_v[o];
   }
 }
-__global__ void k_rows_from_keys32(int rows, long long total, const unsigned* __restrict__ keys, long long* __restrict__ ptr,
-                                   int* __restrict__ len) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_rows_from_keys32(int r0, int rows, long long total, const unsigned* __restrict__ keys,
+                                   long long* __restrict__ ptr, int* __restrict__ len) {
+  const int t = r0 + blockIdx.x * blockDim.x + threadIdx.x;  // rows [r0, rows): the cells this rank's columns of K can name
   if (t > rows) return;
   auto lower = [&](unsigned target) {
     long long lo = 0, hi = total;
@@ -280,10 +226,10 @@ __global__ void k_run_sum(long long total, const unsigned long long* __restrict_
   out_val[o] = acc;
 }
 // row bounds of the compacted, (cell << kbits | archetype)-sorted entries; `total` is read from device memory
-__global__ void k_rows_from_ckeys(int rows, const long long* __restrict__ total_dev,
+__global__ void k_rows_from_ckeys(int r0, int rows, const long long* __restrict__ total_dev,
                                   const unsigned long long* __restrict__ ckeys, int kbits, long long* __restrict__ ptr,
                                   int* __restrict__ len) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (t > rows) return;
   const long long total = *total_dev;
   auto lower = [&](unsigned long long target) {
@@ -320,6 +266,60 @@ __global__ void k_b_support_bits(int k, int S, const int* __restrict__ b_idx, co
   if (sl >= b_cnt[a]) return;
   const int c = b_idx[e];
   atomicOr(&bits[c >> 5], 1u << (c & 31));
+}
+// rows [r0, r1) of L -> this rank's segment of the job-wide layout: entries packed from `base` on, ptr/len at the row's
+// global index (rows r1 .. r0 + slab of a short last slab get empty lists)
+__global__ void k_compact_segment(int r0, int r1, int slab, RowLists L, const unsigned* __restrict__ keep,
+                                  const long long* __restrict__ loc_off, long long base, long long* __restrict__ g_ptr,
+                                  int* __restrict__ g_len, int* __restrict__ g_key, double* __restrict__ g_val) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= slab) return;
+  const int i = r0 + w;
+  const long long o = base + loc_off[w];
+  int len = 0;
+  if (i < r1 && (!keep || ((keep[i >> 5] >> (i & 31)) & 1u))) {
+    len = L.len[i];
+    const long long p = L.ptr[i];
+    for (int x = lane; x < len; x += 32) {
+      g_key[o + x] = L.key[p + x];
+      g_val[o + x] = L.val[p + x];
+    }
+  }
+  if (lane == 0) {
+    g_ptr[i] = o;
+    g_len[i] = len;
+  }
+}
+// M restricted to the columns [c0, c1): lengths, then the compacted (column, value) lists (warp per row)
+__global__ void k_filter_cols_count(int n, int c0, int c1, const int* __restrict__ indptr, const int* __restrict__ col,
+                                    int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int c = 0;
+  if (i < n)
+    for (int e = indptr[i]; e < indptr[i + 1]; ++e) c += (col[e] >= c0 && col[e] < c1) ? 1 : 0;
+  out[i] = c;
+}
+__global__ void k_filter_cols_fill(int n, int c0, int c1, const int* __restrict__ indptr, const int* __restrict__ col,
+                                   const double* __restrict__ val, const long long* __restrict__ off,
+                                   int* __restrict__ len, int* __restrict__ key, double* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long o = off[i];
+  for (int e = indptr[i]; e < indptr[i + 1]; ++e)
+    if (col[e] >= c0 && col[e] < c1) {
+      key[o] = col[e];
+      v[o] = val[e];
+      ++o;
+    }
+  len[i] = (int)(o - off[i]);
+}
+__global__ void k_masked_len(int r0, int r1, int slab, const int* __restrict__ len, const unsigned* __restrict__ keep,
+                             int* __restrict__ out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > slab) return;
+  const int i = r0 + w;
+  out[w] = (w < slab && i < r1 && (!keep || ((keep[i >> 5] >> (i & 31)) & 1u))) ? len[i] : 0;
 }
 __global__ void k_csr_as_lists(int n, const int* __restrict__ indptr, long long* __restrict__ ptr, int* __restrict__ len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -695,6 +695,52 @@ __global__ void k_emit_a_pairs(int n, int S, const int* __restrict__ a_idx, cons
     vals[o + s] = a_val[(size_t)warp * S + s];
   }
 }
+// Row-sharded Gram: a rank accumulates the rows t1B[a, :] of its own slab of archetypes [a0, a1) (every entry is still
+// summed whole, in cell order, by exactly one rank), so it transposes only the slots of A that name those archetypes.
+__global__ void k_arch_hist(int n, int S, const int* __restrict__ a_idx, const int* __restrict__ a_cnt,
+                            int* __restrict__ cells_per_arch) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int cnt = a_cnt[warp];
+  for (int s = lane; s < cnt; s += 32) atomicAdd(&cells_per_arch[a_idx[(size_t)warp * S + s]], 1);
+}
+__global__ void k_count_a_range(int n, int S, int a0, int a1, const int* __restrict__ a_idx,
+                                const int* __restrict__ a_cnt, int* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp > n) return;
+  int c = 0;
+  if (warp < n) {
+    const int cnt = a_cnt[warp];
+    for (int s = lane; s < cnt; s += 32) {
+      const int a = a_idx[(size_t)warp * S + s];
+      c += (a >= a0 && a < a1) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if (lane == 0) out[warp] = c;  // out[n] = 0: the scan ends with the total
+}
+__global__ void k_emit_a_pairs_range(int n, int S, int a0, int a1, const int* __restrict__ a_idx,
+                                     const double* __restrict__ a_val, const int* __restrict__ a_cnt,
+                                     const long long* __restrict__ off, unsigned long long* keys, double* vals) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int cnt = a_cnt[warp];
+  long long o = off[warp];
+  for (int s0 = 0; s0 < cnt; s0 += 32) {
+    const int s = s0 + lane;
+    int a = -1;
+    if (s < cnt) a = a_idx[(size_t)warp * S + s];
+    const bool keep = a >= a0 && a < a1;
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const long long pos = o + __popc(ball & ((1u << lane) - 1u));
+      keys[pos] = ((unsigned long long)(unsigned)a << 32) | (unsigned)warp;
+      vals[pos] = a_val[(size_t)warp * S + s];
+    }
+    o += __popc(ball);
+  }
+}
 __global__ void k_row_bounds(int k, const unsigned long long* __restrict__ keys, long long total, long long* rptr) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a > k) return;
@@ -710,12 +756,12 @@ __global__ void k_row_bounds(int k, const unsigned long long* __restrict__ keys,
 // t1B[l][a] = sum_j A[l,j] A[a,j], cells j ascending (the order of scipy's csr_matmat for A @ A.T, cpu.py:480).
 // Rows longer than `hub_thr` cells ("hub" archetypes: low-index archetypes that collect a little weight from almost
 // every cell through the argmin-of-zeros rule) are skipped here and filled by k_gram_mirror / k_gram_hub_tiles.
-__global__ void k_gram(int k, int S, const unsigned char* __restrict__ is_hub, const long long* __restrict__ rptr,
+__global__ void k_gram(int k, int S, int a0, int a1, const unsigned char* __restrict__ is_hub, const long long* __restrict__ rptr,
                        const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
                        const int* __restrict__ a_idx, const double* __restrict__ a_val,
                        const int* __restrict__ a_cnt, double* __restrict__ t1) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= k) return;
+  if (warp >= k || warp < a0 || warp >= a1) return;
   if (is_hub[warp]) return;
   double* row = t1 + (size_t)warp * k;
   for (long long e = rptr[warp]; e < rptr[warp + 1]; ++e) {
@@ -743,16 +789,17 @@ __global__ void k_gram_mirror(int k, int nhub, const int* __restrict__ hubs, con
 constexpr int GRAM_HUB_MAX = 160;
 constexpr int GRAM_HUB_CELLS = 4096;
 __global__ void __launch_bounds__(256)
-k_gram_hub_tiles(int n, int S, int H, const int* __restrict__ hub_of /* [k] -> hub index or -1 */,
+k_gram_hub_tiles(int n, int S, int H, int tile0, const int* __restrict__ hub_of /* [k] -> hub index or -1 */,
                  const int* __restrict__ a_idx, const double* __restrict__ a_val, const int* __restrict__ a_cnt,
                  double* __restrict__ tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* tile = reinterpret_cast<double*>(smem_raw);            // [H*H]
-  double* hv = tile + (size_t)H * H;                              // [2][FW_SMAX] weights of the staged cell
+  double* tile_acc = reinterpret_cast<double*>(smem_raw);        // [H*H]
+  double* hv = tile_acc + (size_t)H * H;                          // [2][FW_SMAX] weights of the staged cell
   int* hi = reinterpret_cast<int*>(hv + 2 * FW_SMAX);             // [2][FW_SMAX] hub indices
   __shared__ int hcnt[2];
-  for (int t = threadIdx.x; t < H * H; t += 256) tile[t] = 0.0;
-  const int c0 = blockIdx.x * GRAM_HUB_CELLS;
+  for (int t = threadIdx.x; t < H * H; t += 256) tile_acc[t] = 0.0;
+  const int tile = tile0 + blockIdx.x;  // a rank of a sharded job fills its own range of tiles
+  const int c0 = tile * GRAM_HUB_CELLS;
   const int c1 = min(n, c0 + GRAM_HUB_CELLS);
   int buf = 0;
   for (int j = c0; j < c1; ++j, buf ^= 1) {
@@ -782,14 +829,14 @@ k_gram_hub_tiles(int n, int S, int H, const int* __restrict__ hub_of /* [k] -> h
     const int m = hcnt[buf];
     for (int e = threadIdx.x; e < m * m; e += 256) {
       const int p = e / m, q = e - p * m;
-      double* dst = tile + (size_t)hi[buf * FW_SMAX + p] * H + hi[buf * FW_SMAX + q];
+      double* dst = tile_acc + (size_t)hi[buf * FW_SMAX + p] * H + hi[buf * FW_SMAX + q];
       *dst = __dadd_rn(*dst, __dmul_rn(hv[buf * FW_SMAX + p], hv[buf * FW_SMAX + q]));
     }
     // the next iteration stages into the other buffer; its __syncthreads orders these adds before the adds of j+1
   }
   __syncthreads();
-  double* out = tiles + (size_t)blockIdx.x * H * H;
-  for (int t = threadIdx.x; t < H * H; t += 256) out[t] = tile[t];
+  double* out = tiles + (size_t)tile * H * H;
+  for (int t = threadIdx.x; t < H * H; t += 256) out[t] = tile_acc[t];
 }
 __global__ void k_gram_hub_reduce(int k, int H, int ntiles, const int* __restrict__ hubs,
                                   const double* __restrict__ tiles, double* __restrict__ t1) {
@@ -1144,6 +1191,20 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   const double bound = (round == 0) ? FW_INF : bound_v[a];
   const int e_begin = (round == 1 && chunk == 0) ? g.r0n : 0;
   const int e_end = (round == 0) ? min(nc, g.r0n) : nc;
+  if (round == 1 && e_begin < e_end) {
+    // The list is sorted by decreasing upper word of t2, so every candidate from here on has t2 <= t2_ub (the first
+    // one's upper word with all lower bits set).  If even that cannot beat the bound, the whole chunk - and every later
+    // chunk of this archetype - is out by the first bound, without being read.
+    const long long fb = __double_as_longlong(g.c_t2[c0 + e_begin]) | 0xffffffffll;
+    if (-2.0 * __longlong_as_double(fb) > bound) {
+      if (threadIdx.x == 0) {
+        part_v[chunk_ptr[a] + chunk] = FW_INF;
+        part_i[chunk_ptr[a] + chunk] = 0x7fffffff;
+        if (g.evaluated) atomicAdd(g.evaluated + 2, 1ull);
+      }
+      return;
+    }
+  }
   // phase 1: cheap bound tests, survivors compacted into shared memory
   __shared__ int q_cell[UPB_CHUNK];
   __shared__ double q_t2[UPB_CHUNK];
@@ -1827,7 +1888,10 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   SC_TRY(b_val.ensure(ctx, (size_t)k * S));
   SC_TRY(b_cnt.ensure(ctx, (size_t)k));
   SC_TRY(t1A.ensure(ctx, (size_t)k * k));
-  SC_TRY(t1B.ensure(ctx, (size_t)k * k));
+  {
+    const int w = ctx->world();
+    SC_TRY(t1B.ensure(ctx, (size_t)((k + w - 1) / w) * w * k));  // padded to equal archetype slabs (rows are all-gathered)
+  }
   SC_TRY(percell.ensure(ctx, (size_t)std::max(n, 1024) + 64));
   SC_TRY(scalars.ensure(ctx, 8));
   SC_TRY(slow_list.ensure(ctx, (size_t)n));
@@ -1866,14 +1930,32 @@ int sc_fit::set_kernel(const int* indptr, const int* indices, const double* data
   SC_TRY(sc_sum_f64(ctx, sq.p, scalars.p, (size_t)nnz, tmp));
   SC_CUDA(ctx, cudaMemcpyAsync(&m_fro2, scalars.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // K = M M^T (cpu.py:128,157), rows in first-occurrence order; see "products with K" above
+  // K = M M^T (cpu.py:128,157), rows in first-occurrence order; a rank of a sharded job keeps the columns of its own
+  // slab of cells only (see "products with K" above): K[:, slab] = M (M restricted to the columns of the slab)
   {
     CsrView M{n, m_ptr.p, m_col.p, m_val.p};
     SC_TRY(m_ptr64.ensure(ctx, (size_t)n + 1));
     SC_TRY(m_len.ensure(ctx, (size_t)n + 1));
-    SC_LAUNCH(ctx, k_csr_as_lists, (n + 256) / 256, 256, 0, n, m_ptr.p, m_ptr64.p, m_len.p);
-    RowLists Ml{m_ptr64.p, m_len.p, m_col.p, m_val.p};
-    SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Ml, n, Kl, sp, false, true));
+    if (row_begin == 0 && row_end == n) {
+      SC_LAUNCH(ctx, k_csr_as_lists, (n + 256) / 256, 256, 0, n, m_ptr.p, m_ptr64.p, m_len.p);
+      RowLists Ml{m_ptr64.p, m_len.p, m_col.p, m_val.p};
+      SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Ml, n, Kl, sp, false, true));
+    } else {
+      DBuf<int> fkey;
+      DBuf<double> fval;
+      SC_LAUNCH(ctx, k_filter_cols_count, (n + 256) / 256, 256, 0, n, row_begin, row_end, m_ptr.p, m_col.p, cnt_n.p);
+      SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, m_ptr64.p, (size_t)n + 1, tmp));
+      long long fnnz = 0;
+      SC_CUDA(ctx, cudaMemcpyAsync(&fnnz, m_ptr64.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      SC_TRY(fkey.ensure(ctx, (size_t)fnnz + 1));
+      SC_TRY(fval.ensure(ctx, (size_t)fnnz + 1));
+      SC_LAUNCH(ctx, k_filter_cols_fill, (n + 255) / 256, 256, 0, n, row_begin, row_end, m_ptr.p, m_col.p, m_val.p,
+                m_ptr64.p, m_len.p, fkey.p, fval.p);
+      RowLists Ml{m_ptr64.p, m_len.p, fkey.p, fval.p};
+      SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Ml, n, Kl, sp, false, true));
+      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // fkey / fval go out of scope
+    }
   }
   have_M = true;
   pre_valid = false;
@@ -1953,7 +2035,7 @@ RowLists sc_fit::A_view() const {
 // Z[i, :] = sum over the sources (c, a, w) of w K[c, i] for the kept cells i; rows come out sorted by archetype.
 // has_dups: several sources may share (i, a) (K B: the members of archetype a within two hops of i) and are summed in
 // source order; the one-hot E_t of a Frank-Wolfe step has one source per archetype, so nothing needs summing.
-int sc_fit::push_product(const PushSrc& src, const PushFilter& f, bool has_dups, RowListsBuf& Z) {
+int sc_fit::push_product(const PushSrc& src, bool has_dups, RowListsBuf& Z) {
   const int m = src.m;
   int kbits = 1, nbits = 1;
   while ((1ll << kbits) < k) kbits++;
@@ -1962,87 +2044,90 @@ int sc_fit::push_product(const PushSrc& src, const PushFilter& f, bool has_dups,
   SC_TRY(Z.ptr.ensure(ctx, (size_t)n + 1));
   SC_TRY(Z.len.ensure(ctx, (size_t)n + 1));
   Z.rows = n;
-  if (!has_dups) {
-    // flatten (source, entry) -> 32-bit radix sort by target cell -> gather; insensitive to the skew of the rows of K
-    SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
-    SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
-    SC_LAUNCH(ctx, k_src_len, (m + 256) / 256, 256, 0, src, Kv, ps_cnt.p);
-    SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
-    long long total = 0, kept = 0;
-    SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (total >= (1ll << 32)) SC_FAIL(ctx, SC_ERR_CAPACITY, "push product: more than 2^32 entries in one step");
-    const unsigned fgrid = 148 * 16;  // grid-stride over the flattened entries
-    const bool filtered = !(f.r0 == 0 && f.r1 == n);
-    const int* flags = nullptr;
-    const long long* pos = nullptr;
-    kept = total;
-    if (filtered && total > 0) {
-      SC_TRY(push_flags.ensure(ctx, (size_t)total + 1));
-      SC_TRY(run_pos.ensure(ctx, (size_t)total + 1));
-      SC_LAUNCH(ctx, k_push_flags, fgrid, 256, 0, src, Kv, f, ps_off.p, push_flags.p);
-      SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, push_flags.p, run_pos.p, (size_t)total + 1, tmp));
-      SC_CUDA(ctx, cudaMemcpyAsync(&kept, run_pos.p + total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      flags = push_flags.p;
-      pos = run_pos.p;
-    }
-    last_push_total = kept;
-    SC_TRY(Z.key.ensure(ctx, (size_t)kept + 1));
-    SC_TRY(Z.val.ensure(ctx, (size_t)kept + 1));
-    if (kept == 0) {
-      SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
-      SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
-      return SC_OK;
-    }
-    SC_TRY(pk32_in.ensure(ctx, (size_t)kept + 1));
-    SC_TRY(pk32_out.ensure(ctx, (size_t)kept + 1));
-    SC_TRY(pi32_in.ensure(ctx, (size_t)kept + 1));
-    SC_TRY(pi32_out.ensure(ctx, (size_t)kept + 1));
-    SC_TRY(flat_a.ensure(ctx, (size_t)kept + 1));  // flat (archetype, value) of the emitted entries
-    SC_TRY(pv_in.ensure(ctx, (size_t)kept + 1));
-    SC_LAUNCH(ctx, k_push_keys, fgrid, 256, 0, src, Kv, ps_off.p, flags, pos, pk32_in.p, pi32_in.p, flat_a.p, pv_in.p);
-    SC_TRY(sc_sort_pairs_u32_u32(ctx, pk32_in.p, pk32_out.p, pi32_in.p, pi32_out.p, (size_t)kept, nbits, tmp));
-    SC_LAUNCH(ctx, k_push_gather, fgrid, 256, 0, kept, pi32_out.p, flat_a.p, pv_in.p, Z.key.p, Z.val.p);
-    SC_LAUNCH(ctx, k_rows_from_keys32, (n + 256) / 256, 256, 0, n, kept, pk32_out.p, Z.ptr.p, Z.len.p);
-    return SC_OK;
-  }
+  // flattened (source, entry) pairs: off = exclusive scan of the sources' row lengths in this rank's columns of K
   SC_TRY(ps_cnt.ensure(ctx, (size_t)m + 1));
   SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
-  const unsigned wgrid = (unsigned)((((size_t)m + 1) * 32 + 255) / 256);
-  SC_LAUNCH(ctx, k_push_count, wgrid, 256, 0, src, Kv, f, ps_cnt.p);
+  SC_LAUNCH(ctx, k_src_len, (m + 256) / 256, 256, 0, src, Kv, ps_cnt.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
   long long total = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   last_push_total = total;
+  // rows outside this rank's slab receive nothing: their (empty) lists must still be well formed
+  SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
+  SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
+  SC_TRY(Z.key.ensure(ctx, (size_t)total + 1));
+  SC_TRY(Z.val.ensure(ctx, (size_t)total + 1));
+  if (total == 0) return SC_OK;
+  const unsigned fgrid = 148 * 16;  // grid-stride over the flattened entries
+  const int nrows = row_end - row_begin;
+  if (!has_dups) {
+    if (total >= (1ll << 32)) SC_FAIL(ctx, SC_ERR_CAPACITY, "push product: more than 2^32 entries in one step");
+    SC_TRY(pk32_in.ensure(ctx, (size_t)total + 1));
+    SC_TRY(pk32_out.ensure(ctx, (size_t)total + 1));
+    SC_TRY(pi32_in.ensure(ctx, (size_t)total + 1));
+    SC_TRY(pi32_out.ensure(ctx, (size_t)total + 1));
+    SC_TRY(flat_a.ensure(ctx, (size_t)total + 1));  // flat (archetype, value) of the emitted entries
+    SC_TRY(pv_in.ensure(ctx, (size_t)total + 1));
+    SC_LAUNCH(ctx, k_push_keys, fgrid, 256, 0, src, Kv, ps_off.p, pk32_in.p, pi32_in.p, flat_a.p, pv_in.p);
+    SC_TRY(sc_sort_pairs_u32_u32(ctx, pk32_in.p, pk32_out.p, pi32_in.p, pi32_out.p, (size_t)total, nbits, tmp));
+    SC_LAUNCH(ctx, k_push_gather, fgrid, 256, 0, total, pi32_out.p, flat_a.p, pv_in.p, Z.key.p, Z.val.p);
+    SC_LAUNCH(ctx, k_rows_from_keys32, (nrows + 256) / 256, 256, 0, row_begin, row_end, total, pk32_out.p, Z.ptr.p,
+              Z.len.p);
+    return SC_OK;
+  }
   SC_TRY(pk_keys_in.ensure(ctx, (size_t)total + 1));
   SC_TRY(pk_keys_out.ensure(ctx, (size_t)total + 1));
   SC_TRY(pv_in.ensure(ctx, (size_t)total + 1));
-  SC_TRY(Z.key.ensure(ctx, (size_t)total + 1));
-  SC_TRY(Z.val.ensure(ctx, (size_t)total + 1));
-  if (total == 0) {
-    SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
-    SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
-    return SC_OK;
-  }
-  SC_LAUNCH(ctx, k_push_emit, wgrid, 256, 0, src, Kv, f, ps_off.p, kbits, pk_keys_in.p, pv_in.p);
-  const unsigned egrid = (unsigned)((total + 256) / 256);
   SC_TRY(pv_out.ensure(ctx, (size_t)total + 1));
   SC_TRY(run_heads.ensure(ctx, (size_t)total + 1));
   SC_TRY(run_pos.ensure(ctx, (size_t)total + 1));
   SC_TRY(ckeys.ensure(ctx, (size_t)total + 1));
+  SC_LAUNCH(ctx, k_push_emit, fgrid, 256, 0, src, Kv, ps_off.p, kbits, pk_keys_in.p, pv_in.p);
+  const unsigned egrid = (unsigned)((total + 256) / 256);
   SC_TRY(sc_sort_pairs_u64_f64(ctx, pk_keys_in.p, pk_keys_out.p, pv_in.p, pv_out.p, (size_t)total, kbits + nbits, tmp, 0));
   SC_LAUNCH(ctx, k_run_heads, egrid, 256, 0, total, pk_keys_out.p, run_heads.p);
   SC_TRY(sc_exclusive_scan_i64(ctx, run_heads.p, run_pos.p, (size_t)total + 1, tmp));
   SC_LAUNCH(ctx, k_run_sum, egrid, 256, 0, total, pk_keys_out.p, pv_out.p, run_pos.p, kbits, ckeys.p, Z.key.p, Z.val.p);
-  SC_LAUNCH(ctx, k_rows_from_ckeys, (n + 256) / 256, 256, 0, n, run_pos.p + total, ckeys.p, kbits, Z.ptr.p, Z.len.p);
+  SC_LAUNCH(ctx, k_rows_from_ckeys, (nrows + 256) / 256, 256, 0, row_begin, row_end, run_pos.p + total, ckeys.p, kbits,
+            Z.ptr.p, Z.len.p);
   return SC_OK;
 }
 
-// K B rows for the current B (cpu.py:441 `K @ B`), sorted by archetype, for the cells [r0, r1) and - with_support - for
-// the cells of supp(B) wherever they live (t1 = (K B)^T B needs exactly those rows, cpu.py:442)
-int sc_fit::compute_KB(int r0, int r1, bool with_support) {
+// Rows [row_begin, row_end) of L (those whose bit is set in `keep` when it is given) -> job-wide row lists G: every
+// rank packs its rows into its segment of a shared layout (segments padded to the longest one) and the segments are
+// all-gathered, so G holds the selected rows of every rank.  One GPU: G is not used.
+int sc_fit::allgather_rows(const RowLists& L, const unsigned* keep, RowListsBuf& G) {
+  const int w = ctx->world();
+  SC_TRY(t_off.ensure(ctx, (size_t)n + 1));
+  SC_LAUNCH(ctx, k_masked_len, (slab + 256) / 256, 256, 0, row_begin, row_end, slab, L.len, keep, cnt_n.p);
+  SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, t_off.p, (size_t)slab + 1, tmp));
+  SC_TRY(cand_cnt.ensure(ctx, (size_t)w * k + 64));
+  SC_CUDA(ctx, cudaMemcpyAsync(cand_cnt.p + ctx->rank(), t_off.p + slab, sizeof(long long), cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+  SC_TRY(exchange(cand_cnt.p, sizeof(long long)));
+  std::vector<long long> totals((size_t)w);
+  SC_CUDA(ctx, cudaMemcpyAsync(totals.data(), cand_cnt.p, sizeof(long long) * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream));
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  long long seg = 1;
+  for (long long tt : totals) seg = std::max(seg, tt);
+  SC_TRY(G.ptr.ensure(ctx, (size_t)slab * w + 1));
+  SC_TRY(G.len.ensure(ctx, (size_t)slab * w + 1));
+  SC_TRY(G.key.ensure(ctx, (size_t)seg * w));
+  SC_TRY(G.val.ensure(ctx, (size_t)seg * w));
+  G.rows = n;
+  SC_LAUNCH(ctx, k_compact_segment, (unsigned)(((size_t)slab * 32 + 255) / 256), 256, 0, row_begin, row_end, slab, L, keep,
+            t_off.p, (long long)ctx->rank() * seg, G.ptr.p, G.len.p, G.key.p, G.val.p);
+  SC_TRY(exchange(G.ptr.p, sizeof(long long) * (size_t)slab));
+  SC_TRY(exchange(G.len.p, sizeof(int) * (size_t)slab));
+  SC_TRY(exchange(G.key.p, sizeof(int) * (size_t)seg));
+  SC_TRY(exchange(G.val.p, sizeof(double) * (size_t)seg));
+  return SC_OK;
+}
+
+// K B rows of this rank's cells for the current B (cpu.py:441 `K @ B`), sorted by archetype.  with_support: the rows of the
+// cells of supp(B), which t1 = (K B)^T B needs wherever they live (cpu.py:442), are all-gathered into KBs.
+int sc_fit::compute_KB(bool with_support) {
   pstart();
   const int ks = k * S;
   SC_TRY(b_off.ensure(ctx, (size_t)k + 1));
@@ -2056,19 +2141,18 @@ int sc_fit::compute_KB(int r0, int r1, bool with_support) {
   SC_CUDA(ctx, cudaMemcpyAsync(&bnnz, b_off.p + k, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   SC_LAUNCH(ctx, k_b_sources, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_val.p, b_cnt.p, b_off.p, src_cell.p, src_key.p,
             src_w.p);
-  PushFilter f{r0, r1, nullptr};
-  if (with_support && !(r0 == 0 && r1 == n)) {
-    const size_t words = ((size_t)n + 31) / 32;
-    SC_TRY(supp_bits.ensure(ctx, words));
-    SC_CUDA(ctx, cudaMemsetAsync(supp_bits.p, 0, sizeof(unsigned) * words, ctx->stream));
-    SC_LAUNCH(ctx, k_b_support_bits, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_cnt.p, supp_bits.p);
-    f.extra = supp_bits.p;
-  }
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   pstop(P_BROW);
   pstart();
   PushSrc src{(int)bnnz, src_cell.p, src_key.p, src_w.p};
-  SC_TRY(push_product(src, f, true, KB));
+  SC_TRY(push_product(src, true, KB));
+  if (with_support && ctx->world() > 1) {
+    const size_t words = ((size_t)n + 31) / 32;
+    SC_TRY(supp_bits.ensure(ctx, words));
+    SC_CUDA(ctx, cudaMemsetAsync(supp_bits.p, 0, sizeof(unsigned) * words, ctx->stream));
+    SC_LAUNCH(ctx, k_b_support_bits, (ks + 255) / 256, 256, 0, k, S, b_idx.p, b_cnt.p, supp_bits.p);
+    SC_TRY(allgather_rows(KB.view(), supp_bits.p, KBs));
+  }
   pstop(P_SPGEMM_KB);
   return SC_OK;
 }
@@ -2090,8 +2174,7 @@ static void swap_lists(RowListsBuf& a, RowListsBuf& b) {
 int sc_fit::advance_KB(int t) {
   pstart();
   PushSrc src{k, amin_cur.p, nullptr, nullptr};
-  PushFilter f{row_begin, row_end, nullptr};
-  SC_TRY(push_product(src, f, false, DKB));
+  SC_TRY(push_product(src, false, DKB));
   pstop(P_SPGEMM_Y);
   pstart();
   if (t == 1) {
@@ -2148,10 +2231,11 @@ int sc_fit::build_perm() {
 int sc_fit::precompute_A() {
   if (pre_valid) return SC_OK;
   if (!have_M || !have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: kernel matrix and B must be set first");
-  SC_TRY(compute_KB(row_begin, row_end, true));  // this rank's cells (candidates of _updateA, RSS) + supp(B) (t1)
+  SC_TRY(compute_KB(true));  // this rank's cells (candidates of _updateA, RSS); the rows of supp(B) are gathered for t1
   pstart();
   SC_CUDA(ctx, cudaMemsetAsync(t1A.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
-  SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p, KB.view(), t1A.p);
+  SC_LAUNCH(ctx, k_t1A, (k * 32 + 127) / 128, 128, 0, k, S, b_idx.p, b_val.p, b_cnt.p,
+            ctx->world() > 1 ? KBs.view() : KB.view(), t1A.p);
   pstop(P_T1A);
   pre_valid = true;
   return SC_OK;
@@ -2227,11 +2311,21 @@ int sc_fit::update_B_begin() {
   if (!have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: B has not been initialised");
   CsrView M{n, m_ptr.p, m_col.p, m_val.p};
   const int cur = a_cur;
-  // ---- t1B = A A^T: transpose A by a stable sort on (archetype, cell), then accumulate rows in cell order
+  // ---- t1B = A A^T: transpose A by a stable sort on (archetype, cell), then accumulate rows in cell order.
+  // Rows are sharded over the ranks by archetype slab [a0, a1); the slabs are all-gathered (rows of t1B, per-tile hub x hub
+  // partial sums), the mirror and the tile reduction then run on every rank - each entry is produced whole by one rank.
   pstart();
+  const int w = ctx->world();
+  const int ka = (k + w - 1) / w;  // archetypes per rank
+  const int a0 = std::min(k, ctx->rank() * ka), a1 = std::min(k, a0 + ka);
   SC_TRY(a_off.ensure(ctx, (size_t)n + 1));
-  SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, a_cnt[cur].p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-  SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));
+  SC_TRY(arow_ptr.ensure(ctx, (size_t)k + 1));
+  SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p, 0, sizeof(int) * ((size_t)k + 1), ctx->stream));
+  SC_LAUNCH(ctx, k_arch_hist, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, S, a_idx[cur].p, a_cnt[cur].p, cnt_k.p);
+  std::vector<int> cells_per_arch((size_t)k);
+  SC_CUDA(ctx, cudaMemcpyAsync(cells_per_arch.data(), cnt_k.p, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+  SC_LAUNCH(ctx, k_count_a_range, (unsigned)((((size_t)n + 1) * 32 + 255) / 256), 256, 0, n, S, a0, a1, a_idx[cur].p,
+            a_cnt[cur].p, cnt_n.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, a_off.p, (size_t)n + 1, tmp));
   long long annz = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&annz, a_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2240,24 +2334,19 @@ int sc_fit::update_B_begin() {
   SC_TRY(gk_out.ensure(ctx, (size_t)annz + 1));
   SC_TRY(gv_in.ensure(ctx, (size_t)annz + 1));
   SC_TRY(gv_out.ensure(ctx, (size_t)annz + 1));
-  SC_TRY(arow_ptr.ensure(ctx, (size_t)k + 1));
-  SC_LAUNCH(ctx, k_emit_a_pairs, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, S, a_idx[cur].p, a_val[cur].p,
-            a_cnt[cur].p, a_off.p, gk_in.p, gv_in.p);
+  SC_LAUNCH(ctx, k_emit_a_pairs_range, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, S, a0, a1, a_idx[cur].p,
+            a_val[cur].p, a_cnt[cur].p, a_off.p, gk_in.p, gv_in.p);
   int kbits = 1;
   while ((1ll << kbits) < k) kbits++;
   SC_TRY(sc_sort_pairs_u64_f64(ctx, gk_in.p, gk_out.p, gv_in.p, gv_out.p, (size_t)annz, 32 + kbits, tmp));
   SC_LAUNCH(ctx, k_row_bounds, (k + 256) / 256, 256, 0, k, gk_out.p, annz, arow_ptr.p);
-  SC_CUDA(ctx, cudaMemsetAsync(t1B.p, 0, sizeof(double) * (size_t)k * k, ctx->stream));
+  if (a1 > a0) SC_CUDA(ctx, cudaMemsetAsync(t1B.p + (size_t)a0 * k, 0, sizeof(double) * (size_t)(a1 - a0) * k, ctx->stream));
   {
-    // hub rows: found on the host from the row pointers (k+1 values)
+    // hub rows: chosen on the host from the number of cells per archetype (the same on every rank)
     const long long hub_thr = 8192;
-    std::vector<long long> hptr((size_t)k + 1);
-    SC_CUDA(ctx, cudaMemcpyAsync(hptr.data(), arow_ptr.p, sizeof(long long) * ((size_t)k + 1), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<std::pair<long long, int>> cand_h;
     for (int a = 0; a < k; ++a)
-      if (hptr[a + 1] - hptr[a] > hub_thr) cand_h.push_back({-(hptr[a + 1] - hptr[a]), a});
+      if (cells_per_arch[a] > hub_thr) cand_h.push_back({-(long long)cells_per_arch[a], a});
     std::sort(cand_h.begin(), cand_h.end());
     if ((int)cand_h.size() > GRAM_HUB_MAX) cand_h.resize(GRAM_HUB_MAX);  // the rest stay ordinary (sequential) rows
     std::vector<int> hubs;
@@ -2271,21 +2360,28 @@ int sc_fit::update_B_begin() {
     }
     SC_TRY(hub_flag.ensure(ctx, (size_t)k));
     SC_CUDA(ctx, cudaMemcpyAsync(hub_flag.p, ishub.data(), (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
-    SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, hub_flag.p, arow_ptr.p, gk_out.p, gv_out.p, a_idx[cur].p,
-              a_val[cur].p, a_cnt[cur].p, t1B.p);
-    if (!hubs.empty()) {
-      const int H = (int)hubs.size();
-      const int ntiles = (n + GRAM_HUB_CELLS - 1) / GRAM_HUB_CELLS;
+    SC_LAUNCH(ctx, k_gram, (k * 32 + 127) / 128, 128, 0, k, S, a0, a1, hub_flag.p, arow_ptr.p, gk_out.p, gv_out.p,
+              a_idx[cur].p, a_val[cur].p, a_cnt[cur].p, t1B.p);
+    const int H = (int)hubs.size();
+    const int ntiles = (n + GRAM_HUB_CELLS - 1) / GRAM_HUB_CELLS;
+    const int tper = (ntiles + w - 1) / w;  // tiles per rank
+    if (H > 0) {
+      const int tl0 = std::min(ntiles, ctx->rank() * tper), tl1 = std::min(ntiles, tl0 + tper);
       SC_TRY(hub_list.ensure(ctx, (size_t)H));
       SC_TRY(gram_hubof.ensure(ctx, (size_t)k));
-      SC_TRY(gram_tiles.ensure(ctx, (size_t)ntiles * H * H));
+      SC_TRY(gram_tiles.ensure(ctx, (size_t)tper * w * H * H));
       SC_CUDA(ctx, cudaMemcpyAsync(hub_list.p, hubs.data(), sizeof(int) * H, cudaMemcpyHostToDevice, ctx->stream));
       SC_CUDA(ctx, cudaMemcpyAsync(gram_hubof.p, hubof.data(), sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
-      SC_LAUNCH(ctx, k_gram_mirror, dim3((k + 255) / 256, H), 256, 0, k, H, hub_list.p, hub_flag.p, t1B.p);
       const size_t smem = (size_t)H * H * sizeof(double) + 2 * FW_SMAX * (sizeof(double) + sizeof(int));
       SC_CUDA(ctx, cudaFuncSetAttribute(k_gram_hub_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SC_LAUNCH(ctx, k_gram_hub_tiles, ntiles, 256, smem, n, S, H, gram_hubof.p, a_idx[cur].p, a_val[cur].p,
-                a_cnt[cur].p, gram_tiles.p);
+      if (tl1 > tl0)
+        SC_LAUNCH(ctx, k_gram_hub_tiles, tl1 - tl0, 256, smem, n, S, H, tl0, gram_hubof.p, a_idx[cur].p, a_val[cur].p,
+                  a_cnt[cur].p, gram_tiles.p);
+      SC_TRY(exchange(gram_tiles.p, sizeof(double) * (size_t)tper * H * H));
+    }
+    SC_TRY(exchange(t1B.p, sizeof(double) * (size_t)ka * k));
+    if (H > 0) {
+      SC_LAUNCH(ctx, k_gram_mirror, dim3((k + 255) / 256, H), 256, 0, k, H, hub_list.p, hub_flag.p, t1B.p);
       SC_LAUNCH(ctx, k_gram_hub_reduce, (H * H + 255) / 256, 256, 0, k, H, ntiles, hub_list.p, gram_tiles.p, t1B.p);
     }
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
@@ -2296,8 +2392,15 @@ int sc_fit::update_B_begin() {
   RowLists Al{slot_ptr_n.p, a_cnt[cur].p, a_idx[cur].p, a_val[cur].p};
   // rows in first-occurrence order (no compaction, no sort): the values do not depend on the order inside a row of the
   // right-hand side (a key occurs once per row), and the candidate lists are ordered by the radix sort below
-  SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp, false));
-  SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MA.view(), k, T2c, sp, false));  // candidates: this rank's cells only
+  if (ctx->world() == 1) {
+    SC_TRY(sc_spgemm_rows(ctx, M, 0, n, Al, k, MA, sp, false));
+    SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MA.view(), k, T2c, sp, false));
+  } else {
+    // M A^T for this rank's rows only, all-gathered (allgather_rows), so the second product sees every row of M A^T
+    SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, Al, k, MA, sp, false));
+    SC_TRY(allgather_rows(MA.view(), nullptr, MAg));
+    SC_TRY(sc_spgemm_rows(ctx, M, row_begin, row_end, MAg.view(), k, T2c, sp, false));  // candidates: this rank's cells
+  }
   pstop(P_T2ROWS);
   pstart();
   {
@@ -2382,8 +2485,8 @@ int sc_fit::update_B_begin() {
   SC_TRY(cmax_v.ensure(ctx, (size_t)n));
   SC_TRY(cmax_l.ensure(ctx, (size_t)n));
   SC_TRY(bound_v.ensure(ctx, (size_t)2 * k));
-  SC_TRY(eval_cnt.ensure(ctx, 2));
-  SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p, 0, sizeof(unsigned long long) * 2, ctx->stream));
+  SC_TRY(eval_cnt.ensure(ctx, 4));
+  SC_CUDA(ctx, cudaMemsetAsync(eval_cnt.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
   SC_TRY(part_v.ensure(ctx, (size_t)nchunks + 1));
   SC_TRY(part_i.ensure(ctx, (size_t)nchunks + 1));
   SC_LAUNCH(ctx, k_chunk_fill, k, 128, 0, k, chunk_ptr.p, chunk_arch.p);
@@ -2400,9 +2503,9 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   // K B for the current B (cpu.py:486), this rank's rows, first-occurrence order (the rows are only walked here):
   // evaluated from B at the first step, then advanced by the step's rank-k change (see k_kb_merge)
   if (t == 0) {
-    if (!pre_valid) SC_TRY(compute_KB(row_begin, row_end, false));  // else: the rows _updateA / the RSS just used
+    if (!pre_valid) SC_TRY(compute_KB(false));  // else: the rows _updateA / the RSS just used
   } else if (fresh_kb) {
-    SC_TRY(compute_KB(row_begin, row_end, false));
+    SC_TRY(compute_KB(false));
   } else {
     SC_TRY(advance_KB(t));
   }
@@ -2515,9 +2618,13 @@ int sc_fit::update_B_end() {
   in_update_B = false;
   {
     unsigned long long ev = 0;
+    unsigned long long pruned = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&pruned, eval_cnt.p + 2, sizeof(pruned), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyAsync(&ev, eval_cnt.p, sizeof(ev), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     last_evaluated = (long long)ev;
+    last_pruned_chunks = (long long)pruned;
+    last_chunk_launches = nchunks_cur * T;
     for (int t = 0; t < T; ++t) {
       float ms = 0.f;
       SC_CUDA(ctx, cudaEventElapsedTime(&ms, ev_a[t], ev_b[t]));
@@ -2624,12 +2731,14 @@ int sc_fit::get_KB_csr(long long* nnz_out, long long* indptr, int* indices, doub
   if (!have_B) SC_FAIL(ctx, SC_ERR_STATE, "fit: B has not been initialised");
   if (row_begin == 0 && row_end == n) {
     SC_TRY(precompute_A());
-  } else {  // a rank of a sharded job holds K B for its own cells only: evaluate every row for this accessor
-    SC_TRY(compute_KB(0, n, false));
-    pre_valid = false;
+  } else {  // a rank of a sharded job holds K B for its own cells only: gather every row for this accessor
+    SC_TRY(precompute_A());
+    SC_TRY(allgather_rows(KB.view(), nullptr, KBs));
+    pre_valid = false;  // KBs no longer holds the support rows of t1
   }
+  const RowLists KBall = (row_begin == 0 && row_end == n) ? KB.view() : KBs.view();
   SC_TRY(t_off.ensure(ctx, (size_t)n + 1));
-  SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, KB.len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  SC_CUDA(ctx, cudaMemcpyAsync(cnt_n.p, KBall.len, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
   SC_CUDA(ctx, cudaMemsetAsync(cnt_n.p + n, 0, sizeof(int), ctx->stream));
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, t_off.p, (size_t)n + 1, tmp));
   long long nnz = 0;
@@ -2641,7 +2750,7 @@ int sc_fit::get_KB_csr(long long* nnz_out, long long* indptr, int* indices, doub
   DBuf<double> dv;
   SC_TRY(di.ensure(ctx, (size_t)nnz + 1));
   SC_TRY(dv.ensure(ctx, (size_t)nnz + 1));
-  SC_LAUNCH(ctx, k_lists_to_csr, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KB.view(), t_off.p, di.p, dv.p);
+  SC_LAUNCH(ctx, k_lists_to_csr, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, KBall, t_off.p, di.p, dv.p);
   SC_CUDA(ctx, sc_copy(indptr, t_off.p, sizeof(long long) * ((size_t)n + 1), ctx->stream));
   SC_CUDA(ctx, sc_copy(indices, di.p, sizeof(int) * (size_t)nnz, ctx->stream));
   SC_CUDA(ctx, sc_copy(data, dv.p, sizeof(double) * (size_t)nnz, ctx->stream));

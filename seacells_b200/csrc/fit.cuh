@@ -40,16 +40,19 @@ struct sc_fit {
   DBuf<long long> ps_off, run_heads, run_pos;
   DBuf<unsigned long long> pk_keys_in, pk_keys_out, ckeys;
   DBuf<unsigned> supp_bits, pk32_in, pk32_out, pi32_in, pi32_out;
-  DBuf<int> push_flags, flat_a;
+  DBuf<int> flat_a;
   // compressed B
   DBuf<int> b_idx, b_cnt;
   DBuf<double> b_val;
-  // K*B rows
-  RowListsBuf KB;
+  // K*B rows of this rank's cells; KBs: rows gathered from every rank (the support of B for t1, or all rows for Z_)
+  RowListsBuf KB, KBs;
   // incremental K B inside one _updateB call: chosen cells of the last step, K E, second K B buffer
   DBuf<int> amin_cur;
   RowListsBuf DKB, KB2;
-  int r0_seed = 16;  // round 0 of the gradient kernel after step 0: previous winner + this many largest-t2 candidates (0: 64, no seed)
+  // SC_R0_SEED = m > 0: after step 0, round 0 of the gradient kernel evaluates the previous winner + the m largest-t2
+  // candidates instead of the 64 largest.  Measured at 1M cells: m = 16 triples the survivors of round 1 (fit 4.69 s vs
+  // 3.97 s), m = 64 changes nothing - the previous winner is almost always among the 64 anyway.  Off by default.
+  int r0_seed = 0;
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step
@@ -58,7 +61,7 @@ struct sc_fit {
   DBuf<double> bv_in;
   DBuf<double> t1A, t1B;
   // _updateB precompute
-  RowListsBuf MA, T2c;
+  RowListsBuf MA, MAg, T2c;
   DBuf<long long> c_ptr, a_off, arow_ptr, chunk_ptr, t_off, cand_cnt;
   DBuf<unsigned long long> ck_in, ck_out;
   DBuf<unsigned> co_in, co_out;
@@ -69,7 +72,7 @@ struct sc_fit {
   DBuf<int> cmax_l;
   DBuf<unsigned char> hub_flag;
   DBuf<unsigned long long> eval_cnt;
-  long long last_evaluated = 0;
+  long long last_evaluated = 0, last_pruned_chunks = 0, last_chunk_launches = 0;
   // CUDA-event timing of the dominant kernel (k_updateB_eval, both rounds of one Frank-Wolfe step), always on
   std::vector<cudaEvent_t> ev_a, ev_b, ev_h0, ev_h1;
   double hub_ms_total = 0.0, hub_bytes_total = 0.0;  // k_updateB_hub alone (incremental launches)
@@ -103,8 +106,9 @@ struct sc_fit {
   int set_A_lists(const long long* colptr, const int* idx, const double* val);
   int set_A_slots(const int* idx, const double* val, const int* cnt);
   RowLists A_view() const;
-  int push_product(const struct PushSrc& src, const struct PushFilter& f, bool has_dups, RowListsBuf& Z);
-  int compute_KB(int r0, int r1, bool with_support);
+  int push_product(const struct PushSrc& src, bool has_dups, RowListsBuf& Z);
+  int allgather_rows(const RowLists& L, const unsigned* keep, RowListsBuf& G);
+  int compute_KB(bool with_support);
   int advance_KB(int t);
   int build_perm();
   int update_B_begin();

@@ -74,11 +74,11 @@ def _knn_roofline(n, d, world, filter_s, kind, kp, fallback_rows):
 
 
 def _traffic(n, world):
-    """DRAM bytes per launch group from the committed ncu --set full capture (1M cells, 1 GPU only)."""
-    p = os.path.join(ROOT, "profiles", "r1_updB_group_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (1M cells, 1 GPU only)."""
+    p = os.path.join(ROOT, "profiles", "r2_hub_kernel_traffic.json")
     if n == 1_000_000 and world == 1 and os.path.exists(p):
         try:
-            return float(json.load(open(p))["dram_bytes_per_launch_group"])
+            return float(json.load(open(p))["dram_bytes_per_launch"])
         except Exception:
             return None
     return None
@@ -328,23 +328,41 @@ def run_ours(args):
     extras = {} if args.no_extras else _extras(args, ctx, lib_stream, X, M, arch, A0, A0_raw, world, eng, rss, labels_sha)
     value = n * args.steps / t_dev      # whole job: one n-cell fit per step, however many GPUs share it
     e2e = n * args.steps / t_e2e
-    # roofline of the dominant kernel: gradient evaluation of _updateB (k_row_max + k_updateB_eval x2 per FW step)
+    # roofline of the dominant kernel.  Largest single kernel of the fit by time: k_updateB_hub, the cell-major gradient of
+    # the hub archetypes, one launch per Frank-Wolfe step (CUDA events on the library's stream around that launch alone).
+    # Algorithmic bytes per launch: 24 B x cells x hub archetypes (running product read + written, t2 read)
+    # + 12 B x delta entries of the step.  The launch group it belongs to (row maxima, both rounds of k_updateB_eval, hub
+    # kernel + reduction) is reported next to it with the byte count of round 1.
+    peak, peak_src = _peaks()
+    hub_steps = st1["hub_steps_timed"] - st0["hub_steps_timed"]
+    hub_s = (st1["hub_ns_total"] - st0["hub_ns_total"]) / 1e9
+    hub_launch_s = hub_s / max(hub_steps, 1)
+    hub_bytes = float(st1["hub_bytes_per_launch"])
+    hub_gbs = hub_bytes / hub_launch_s / 1e9 if hub_launch_s > 0 else 0.0
     steps_timed = st1["updB_steps_timed"] - st0["updB_steps_timed"]
     eval_s = (st1["updB_eval_ns_total"] - st0["updB_eval_ns_total"]) / 1e9
     per_launch_s = eval_s / max(steps_timed, 1)
     alg_bytes = 12.0 * st1["t2_nnz_last_update_B"] + 12.0 * st1["kb_nnz_last"] + 16.0 * n / world  # rank 0's shard
-    peak, peak_src = _peaks()
-    achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    grp_gbs = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     roofline = {"bound": "hbm",
-                "kernel": "gradient of _updateB on the support of t2: k_row_max + k_updateB_eval (2 rounds) + "
-                          "k_updateB_hub (+reduce), one launch group per Frank-Wolfe step",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(n, world),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_ms": per_launch_s * 1e3, "launches_timed": steps_timed,
-                "share_of_step": eval_s / t_dev if t_dev > 0 else None,
-                "bytes_definition": "12 B x nnz(t2) candidate (cell, t2) pairs + 12 B x nnz(K B) row entries + 16 B x n "
-                                    "row maxima, each moved once per Frank-Wolfe step (rank 0's shard when N > 1)",
-                "traffic_note": "ncu dram bytes of the two largest kernels of the group are in profiles/*.summary.txt"}
+                "kernel": "k_updateB_hub (gradient of _updateB for the hub archetypes, cell-major; incremental launches)",
+                "achieved": hub_gbs, "peak": peak, "unit": "GB/s", "frac": hub_gbs / peak, "traffic": _traffic(n, world),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": hub_bytes,
+                "avg_launch_ms": hub_launch_s * 1e3, "launches_timed": hub_steps,
+                "share_of_step": hub_s / t_dev if t_dev > 0 else None,
+                "bytes_definition": "24 B x cells x hub archetypes (HH read + write, t2 read; 8 B each) + 12 B x delta "
+                                    "entries of the step (rank 0's shard when N > 1)",
+                "launch_group": {"what": "gradient of _updateB, all archetypes: k_row_max (steps 0-1) + k_updateB_eval x 2 + "
+                                         "k_updateB_hub + reduction, one group per Frank-Wolfe step",
+                                 "avg_group_ms": per_launch_s * 1e3, "groups_timed": steps_timed,
+                                 "share_of_step": eval_s / t_dev if t_dev > 0 else None,
+                                 "round1_definition_bytes": alg_bytes, "round1_definition_GBps": grp_gbs,
+                                 "round1_definition_frac": grp_gbs / peak,
+                                 "note": "round-1 definition = 12 B x nnz(t2) + 12 B x nnz(K B) + 16 B x n per group; since "
+                                         "the sorted-list bound discards most 1024-candidate chunks unread "
+                                         f"({st1['chunks_pruned_unread_last_update_B']} of "
+                                         f"{st1['chunk_launches_last_update_B']} in the last _updateB) those bytes are "
+                                         "no longer all moved - kept for comparison with round 1 only"}}
     cpu_n = 4000
     cpu_dt, cpu_iters, cpu_k = cpu_fit_sample(cpu_n)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -7,6 +7,7 @@ package works without it, using it raises `SeacellsB200Error`.
 """
 from ._lib import SeacellsB200Error  # noqa: F401
 from .core import FitEngine, KernelMatrix, SEACells, SEACellsB200, build_kernel, knn, spmm_csr  # noqa: F401
+from . import evaluate  # noqa: F401
 from .summarize import sparsify_assignments, summarize_by_SEACell, summarize_by_soft_SEACell  # noqa: F401
 
 __version__ = "0.1.0"

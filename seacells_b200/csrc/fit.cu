@@ -966,21 +966,34 @@ __global__ void __launch_bounds__(256, 2) k_updateB_hub(int row_begin, int row_e
   }
   const int c0 = row_begin + blockIdx.x * HUB_CELLS_PER_CTA;
   const int c1 = min(row_end, c0 + HUB_CELLS_PER_CTA);
+  // Software pipeline over the warp's groups of HUB_UNROLL cells: the cell ids of the group after next and the list
+  // headers of the next group are requested while the current group is processed, so the dependent chain
+  // perm -> (ptr, len) -> entries -> t1 rows no longer starts from scratch in every iteration.
+  int n_cell[HUB_UNROLL], n_L[HUB_UNROLL], nn_cell[HUB_UNROLL];
+  long long n_p[HUB_UNROLL];
+  {
+    const int i0 = c0 + warp * HUB_UNROLL;
+#pragma unroll
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      n_cell[u] = (i0 + u < c1) ? perm[i0 + u - row_begin] : -1;
+      nn_cell[u] = (i0 + 8 * HUB_UNROLL + u < c1) ? perm[i0 + 8 * HUB_UNROLL + u - row_begin] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < HUB_UNROLL; ++u) {
+      n_p[u] = n_cell[u] >= 0 ? KB.ptr[n_cell[u]] : 0;
+      n_L[u] = n_cell[u] >= 0 ? KB.len[n_cell[u]] : 0;
+    }
+  }
   for (int ii = c0 + warp * HUB_UNROLL; ii < c1; ii += 8 * HUB_UNROLL) {
     int cell[HUB_UNROLL], L[HUB_UNROLL];
     long long p[HUB_UNROLL];
     double hh[HUB_UNROLL][R], t2[HUB_UNROLL][R], acc[HUB_UNROLL][R];
 #pragma unroll
     for (int u = 0; u < HUB_UNROLL; ++u) {
-      cell[u] = (ii + u < c1) ? perm[ii + u - row_begin] : -1;  // locality order; ties are resolved on the cell index
-    }
-#pragma unroll
-    for (int u = 0; u < HUB_UNROLL; ++u) {
-      p[u] = 0;
-      L[u] = 0;
+      cell[u] = n_cell[u];  // locality order; ties are resolved on the cell index
+      p[u] = n_p[u];
+      L[u] = n_L[u];
       if (cell[u] >= 0) {
-        p[u] = KB.ptr[cell[u]];
-        L[u] = KB.len[cell[u]];
         const size_t ro = (size_t)(cell[u] - row_begin) * nh_pad + lane;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -990,6 +1003,14 @@ __global__ void __launch_bounds__(256, 2) k_updateB_hub(int row_begin, int row_e
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[u][r] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < HUB_UNROLL; ++u) {  // prefetch: headers of the next group, cell ids of the one after
+      n_cell[u] = nn_cell[u];
+      n_p[u] = n_cell[u] >= 0 ? KB.ptr[n_cell[u]] : 0;
+      n_L[u] = n_cell[u] >= 0 ? KB.len[n_cell[u]] : 0;
+      const int j = ii + 16 * HUB_UNROLL + u;
+      nn_cell[u] = (j < c1) ? perm[j - row_begin] : -1;
     }
 #pragma unroll
     for (int u = 0; u < HUB_UNROLL; ++u) {

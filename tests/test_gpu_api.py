@@ -223,3 +223,36 @@ def test_two_devices_in_one_process():
             assert torch.cuda.current_device() == 1 - dv
     assert same_sparse(engines[0].A(), engines[1].A()) and same_sparse(engines[0].B(), engines[1].B())
     assert engines[0].rss() == engines[1].rss()
+
+
+def test_evaluate_compactness_and_separation():
+    """evaluate.py:6-81 on injected diffusion components (palantir is third party): group statistics as pandas computes
+    them, nearest-metacell distances as sklearn's brute-force NearestNeighbors returns them."""
+    import pandas as pd
+    from sklearn.neighbors import NearestNeighbors
+    from seacells_b200 import evaluate
+    from seacells_b200.synth import MiniAnnData, synth_embedding
+    n, k = 3000, 40
+    X = synth_embedding(n, 50, 9)
+    rng = np.random.default_rng(3)
+    dc = rng.normal(size=(n, 10)) * np.linspace(2.0, 0.2, 10)
+    ad = MiniAnnData(X)
+    ad.obs["SEACell"] = [f"SEACell-{i}" for i in rng.integers(0, k, size=n)]
+    ad.obs["celltype"] = rng.choice(["a", "b", "c"], size=n)
+    df = pd.DataFrame(dc, index=ad.obs_names).join(ad.obs["SEACell"])
+    comp = evaluate.compactness(ad, diffusion_components=dc)
+    np.testing.assert_allclose(comp["compactness"].values, df.groupby("SEACell").var().mean(1).values, rtol=1e-12)
+    cent = df.groupby("SEACell").mean()
+    for nth in (1, 3):
+        sep = evaluate.separation(ad, nth_nbr=nth, diffusion_components=dc)
+        ref = NearestNeighbors(n_neighbors=nth, algorithm="brute").fit(cent.values).kneighbors()[0][:, nth - 1]
+        assert list(sep.index) == list(cent.index)
+        # the reference renames column 1 only (evaluate.py:79-81): for nth_nbr != 1 the column keeps the name nth_nbr
+        assert list(sep.columns) == (["separation"] if nth == 1 else [nth])
+        np.testing.assert_allclose(sep.iloc[:, 0].values, ref, rtol=1e-8)  # sklearn expands ||x-y||^2 (less exact)
+    sep_c = evaluate.separation(ad, nth_nbr=1, cluster="celltype", diffusion_components=dc)
+    assert 0 < len(sep_c) <= k
+    pur = evaluate.compute_celltype_purity(ad, "celltype")
+    assert pur.shape == (k, 2) and (pur["celltype_purity"] <= 1).all()
+    with pytest.raises(ImportError):
+        evaluate.compactness(ad)           # palantir is not installed here: clear error, no silent fallback

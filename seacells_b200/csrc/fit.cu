@@ -22,6 +22,8 @@
 #include "comm.cuh"
 #include "fit_kernels.cuh"
 
+constexpr long long SYNC_FREE_CAP = 4ll << 20;  // entries; see push_product
+
 // ------------------------------------------------------------------------------------------------ small kernels
 __global__ void k_fill_stride_ptr(long long* p, int rows, int stride) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,9 +181,11 @@ k_push_keys(PushSrc src, RowLists K, const long long* __restrict__ off, unsigned
 }
 // sorted position j -> (archetype, value) of the emitted entry idx[j]
 __global__ void __launch_bounds__(256)
-k_push_gather(long long kept, const unsigned* __restrict__ idx, const int* __restrict__ flat_a,
-              const double* __restrict__ flat_v, int* __restrict__ z_key, double* __restrict__ z_val) {
+k_push_gather(long long kept, const unsigned* __restrict__ keys, const unsigned* __restrict__ idx,
+              const int* __restrict__ flat_a, const double* __restrict__ flat_v, int* __restrict__ z_key,
+              double* __restrict__ z_val) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < kept; j += (long long)gridDim.x * blockDim.x) {
+    if (keys[j] == 0xffffffffu) continue;  // sentinel of the sync-free variant (unused sort slot)
     const unsigned o = idx[j];
     z_key[j] = flat_a[o];
     z_val[j] = flat_v[o];
@@ -320,6 +324,13 @@ __global__ void k_masked_len(int r0, int r1, int slab, const int* __restrict__ l
   if (w > slab) return;
   const int i = r0 + w;
   out[w] = (w < slab && i < r1 && (!keep || ((keep[i >> 5] >> (i & 31)) & 1u))) ? len[i] : 0;
+}
+__global__ void k_max_int(int n, const int* __restrict__ v, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = (i < n) ? v[i] : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 __global__ void k_csr_as_lists(int n, const int* __restrict__ indptr, long long* __restrict__ ptr, int* __restrict__ len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -697,10 +708,10 @@ __global__ void k_emit_a_pairs(int n, int S, const int* __restrict__ a_idx, cons
 }
 // Row-sharded Gram: a rank accumulates the rows t1B[a, :] of its own slab of archetypes [a0, a1) (every entry is still
 // summed whole, in cell order, by exactly one rank), so it transposes only the slots of A that name those archetypes.
-__global__ void k_arch_hist(int n, int S, const int* __restrict__ a_idx, const int* __restrict__ a_cnt,
+__global__ void k_arch_hist(int r0, int r1, int S, const int* __restrict__ a_idx, const int* __restrict__ a_cnt,
                             int* __restrict__ cells_per_arch) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
+  const int warp = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= r1) return;
   const int cnt = a_cnt[warp];
   for (int s = lane; s < cnt; s += 32) atomicAdd(&cells_per_arch[a_idx[(size_t)warp * S + s]], 1);
 }
@@ -787,7 +798,7 @@ __global__ void k_gram_mirror(int k, int nhub, const int* __restrict__ hubs, con
 // puts on hub archetypes are staged in shared memory and all pairs are added into the CTA's private H x H tile (targets
 // of one cell are distinct, cells are sequential => fixed order).  The per-CTA tiles are then summed in CTA order.
 constexpr int GRAM_HUB_MAX = 160;
-constexpr int GRAM_HUB_CELLS = 4096;
+constexpr int GRAM_HUB_CELLS = 1024;  // cells per hub x hub tile (a CTA walks them one after the other)
 __global__ void __launch_bounds__(256)
 k_gram_hub_tiles(int n, int S, int H, int tile0, const int* __restrict__ hub_of /* [k] -> hub index or -1 */,
                  const int* __restrict__ a_idx, const double* __restrict__ a_val, const int* __restrict__ a_cnt,
@@ -1113,6 +1124,14 @@ __global__ void __launch_bounds__(256) k_updateB_hub_reduce(int nctas, int nh_pa
     o[3] = res[3];
   }
 }
+// job-wide pruning bound: minimum over the ranks of the round-0 minima (all-gathered, [world][k])
+__global__ void k_min_over_ranks(int k, int world, const double* __restrict__ all, double* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= k) return;
+  double m = all[a];
+  for (int r = 1; r < world; ++r) m = fmin(m, all[(size_t)r * k + a]);
+  out[a] = m;
+}
 __global__ void k_chunk_fill(int k, const long long* __restrict__ chunk_ptr, int* __restrict__ chunk_arch) {
   const int a = blockIdx.x;
   for (long long c = chunk_ptr[a] + threadIdx.x; c < chunk_ptr[a + 1]; c += blockDim.x) chunk_arch[c] = a;
@@ -1193,14 +1212,18 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
                                                       const int* __restrict__ chunk_arch,
                                                       const double* __restrict__ cmax_v, const int* __restrict__ cmax_l,
                                                       double* __restrict__ part_v, int* __restrict__ part_i,
-                                                      double* __restrict__ bound_v) {
+                                                      double* __restrict__ bound_v,
+                                                      const double* __restrict__ prune_bound) {
   __shared__ double sg[8];
   __shared__ int si[8];
   int a, chunk;
   if (round == 0) {
     a = blockIdx.x;
     chunk = 0;
-    if (chunk_ptr[a + 1] == chunk_ptr[a]) return;
+    if (chunk_ptr[a + 1] == chunk_ptr[a]) {  // no candidates of this archetype on this rank (or a hub archetype)
+      if (threadIdx.x == 0) bound_v[a] = FW_INF;  // the bounds are all-gathered: never leave a stale one behind
+      return;
+    }
   } else {
     a = chunk_arch[blockIdx.x];
     chunk = (int)((long long)blockIdx.x - chunk_ptr[a]);
@@ -1209,7 +1232,7 @@ __global__ void __launch_bounds__(256) k_updateB_eval(UpdBArgs g, int round, con
   const double* __restrict__ row = g.t1 + (size_t)a * g.k;
   const long long c0 = g.c_ptr[a] + (long long)chunk * UPB_CHUNK;
   const int nc = (int)min((long long)UPB_CHUNK, g.c_ptr[a + 1] - c0);
-  const double bound = (round == 0) ? FW_INF : bound_v[a];
+  const double bound = (round == 0) ? FW_INF : prune_bound[a];  // job-wide: the smallest round-0 minimum of any rank
   const int e_begin = (round == 1 && chunk == 0) ? g.r0n : 0;
   const int e_end = (round == 0) ? min(nc, g.r0n) : nc;
   if (round == 1 && e_begin < e_end) {
@@ -1335,6 +1358,7 @@ __global__ void __launch_bounds__(256) k_updateB_local(UpdBArgs g, int row_begin
                                                        const double* __restrict__ part_v,
                                                        const int* __restrict__ part_i,
                                                        const double* __restrict__ bound_v,
+                                                       const double* __restrict__ prune_bound,
                                                        const int* __restrict__ hub_slot, double* __restrict__ out) {
   __shared__ double sg[8];
   __shared__ int si[8];
@@ -1362,7 +1386,9 @@ __global__ void __launch_bounds__(256) k_updateB_local(UpdBArgs g, int row_begin
   double nv = FW_INF;
   int ni = 0x7fffffff;
   const long long ncand = g.c_ptr[a + 1] - g.c_ptr[a];
-  if (!(bv < 0.0) && ncand < (long long)(row_end - row_begin)) {
+  // (a negative job-wide bound means some rank holds a negative candidate: the column argmin is a candidate, and the
+  // scan of this rank's cells outside the support would be thrown away by the merge)
+  if (!(bv < 0.0) && !(prune_bound[a] < 0.0) && ncand < (long long)(row_end - row_begin)) {
     double tv = FW_INF;
     int ti = 0x7fffffff;
     bool found = false;
@@ -1978,6 +2004,12 @@ int sc_fit::set_kernel(const int* indptr, const int* indices, const double* data
       SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // fkey / fval go out of scope
     }
   }
+  {
+    SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
+    SC_LAUNCH(ctx, k_max_int, (n + 255) / 256, 256, 0, n, Kl.len.p, slow_cnt.p);
+    SC_CUDA(ctx, cudaMemcpyAsync(&k_maxrow, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   have_M = true;
   pre_valid = false;
   return SC_OK;
@@ -2070,10 +2102,18 @@ int sc_fit::push_product(const PushSrc& src, bool has_dups, RowListsBuf& Z) {
   SC_TRY(ps_off.ensure(ctx, (size_t)m + 1));
   SC_LAUNCH(ctx, k_src_len, (m + 256) / 256, 256, 0, src, Kv, ps_cnt.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, ps_cnt.p, ps_off.p, (size_t)m + 1, tmp));
-  long long total = 0;
-  SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // Small problems are launch- and sync-bound (a 10k-cell fit is 500 Frank-Wolfe steps of ~16 tiny kernels): when the
+  // bound m x (longest row of K) is small, the per-step product is sized by that bound and runs without reading the
+  // exact count back - unused sort slots hold a sentinel key that sorts behind every cell.
+  const long long cap = (long long)m * std::max(k_maxrow, 1);
+  const bool sync_free = !has_dups && cap <= SYNC_FREE_CAP;
+  long long total = cap;
+  if (!sync_free) {
+    SC_CUDA(ctx, cudaMemcpyAsync(&total, ps_off.p + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   last_push_total = total;
+  last_push_sync_free = sync_free;
   // rows outside this rank's slab receive nothing: their (empty) lists must still be well formed
   SC_CUDA(ctx, cudaMemsetAsync(Z.ptr.p, 0, sizeof(long long) * ((size_t)n + 1), ctx->stream));
   SC_CUDA(ctx, cudaMemsetAsync(Z.len.p, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
@@ -2090,9 +2130,11 @@ int sc_fit::push_product(const PushSrc& src, bool has_dups, RowListsBuf& Z) {
     SC_TRY(pi32_out.ensure(ctx, (size_t)total + 1));
     SC_TRY(flat_a.ensure(ctx, (size_t)total + 1));  // flat (archetype, value) of the emitted entries
     SC_TRY(pv_in.ensure(ctx, (size_t)total + 1));
+    if (sync_free) SC_CUDA(ctx, cudaMemsetAsync(pk32_in.p, 0xff, sizeof(unsigned) * (size_t)total, ctx->stream));
     SC_LAUNCH(ctx, k_push_keys, fgrid, 256, 0, src, Kv, ps_off.p, pk32_in.p, pi32_in.p, flat_a.p, pv_in.p);
-    SC_TRY(sc_sort_pairs_u32_u32(ctx, pk32_in.p, pk32_out.p, pi32_in.p, pi32_out.p, (size_t)total, nbits, tmp));
-    SC_LAUNCH(ctx, k_push_gather, fgrid, 256, 0, total, pi32_out.p, flat_a.p, pv_in.p, Z.key.p, Z.val.p);
+    SC_TRY(sc_sort_pairs_u32_u32(ctx, pk32_in.p, pk32_out.p, pi32_in.p, pi32_out.p, (size_t)total, sync_free ? 32 : nbits,
+                                 tmp));
+    SC_LAUNCH(ctx, k_push_gather, fgrid, 256, 0, total, pk32_out.p, pi32_out.p, flat_a.p, pv_in.p, Z.key.p, Z.val.p);
     SC_LAUNCH(ctx, k_rows_from_keys32, (nrows + 256) / 256, 256, 0, row_begin, row_end, total, pk32_out.p, Z.ptr.p,
               Z.len.p);
     return SC_OK;
@@ -2207,10 +2249,14 @@ int sc_fit::advance_KB(int t) {
     SC_TRY(KB2.len.ensure(ctx, (size_t)n));
     SC_LAUNCH(ctx, k_merge_len, (n + 256) / 256, 256, 0, n, KB.len.p, DKB.len.p, sp.ub.p);
     SC_TRY(sc_exclusive_scan_i64(ctx, sp.ub.p, KB2.ptr.p, (size_t)n + 1, sp.tmp));
-    long long total = 0;
-    SC_CUDA(ctx, cudaMemcpyAsync(&total, KB2.ptr.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaMemsetAsync(KB2.len.p, 0, sizeof(int) * (size_t)n, ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long total = 0;
+    if (last_push_sync_free) {
+      total = (long long)T * last_push_total;  // nnz(K B_t) <= t x (bound of one step's delta): sized once, no read-back
+    } else {
+      SC_CUDA(ctx, cudaMemcpyAsync(&total, KB2.ptr.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+      SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     SC_TRY(KB2.key.ensure(ctx, (size_t)total + 1));
     SC_TRY(KB2.val.ensure(ctx, (size_t)total + 1));
     KB2.rows = n;
@@ -2341,16 +2387,27 @@ int sc_fit::update_B_begin() {
   const int a0 = std::min(k, ctx->rank() * ka), a1 = std::min(k, a0 + ka);
   SC_TRY(a_off.ensure(ctx, (size_t)n + 1));
   SC_TRY(arow_ptr.ensure(ctx, (size_t)k + 1));
-  SC_CUDA(ctx, cudaMemsetAsync(cnt_k.p, 0, sizeof(int) * ((size_t)k + 1), ctx->stream));
-  SC_LAUNCH(ctx, k_arch_hist, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, S, a_idx[cur].p, a_cnt[cur].p, cnt_k.p);
-  std::vector<int> cells_per_arch((size_t)k);
-  SC_CUDA(ctx, cudaMemcpyAsync(cells_per_arch.data(), cnt_k.p, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+  // cells per archetype (hub selection): counted on this rank's cells, the counts are all-gathered and summed on the host
+  SC_TRY(arch_cnt_all.ensure(ctx, (size_t)w * k));
+  {
+    int* mine = arch_cnt_all.p + (size_t)ctx->rank() * k;
+    const int nloc = row_end - row_begin;
+    SC_CUDA(ctx, cudaMemsetAsync(mine, 0, sizeof(int) * (size_t)k, ctx->stream));
+    if (nloc > 0)
+      SC_LAUNCH(ctx, k_arch_hist, (unsigned)(((size_t)nloc * 32 + 255) / 256), 256, 0, row_begin, row_end, S, a_idx[cur].p,
+                a_cnt[cur].p, mine);
+    SC_TRY(exchange(arch_cnt_all.p, sizeof(int) * (size_t)k));
+  }
+  std::vector<int> cnt_all((size_t)w * k), cells_per_arch((size_t)k, 0);
+  SC_CUDA(ctx, cudaMemcpyAsync(cnt_all.data(), arch_cnt_all.p, sizeof(int) * cnt_all.size(), cudaMemcpyDeviceToHost, ctx->stream));
   SC_LAUNCH(ctx, k_count_a_range, (unsigned)((((size_t)n + 1) * 32 + 255) / 256), 256, 0, n, S, a0, a1, a_idx[cur].p,
             a_cnt[cur].p, cnt_n.p);
   SC_TRY(sc_exclusive_scan_i32_to_i64(ctx, cnt_n.p, a_off.p, (size_t)n + 1, tmp));
   long long annz = 0;
   SC_CUDA(ctx, cudaMemcpyAsync(&annz, a_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < w; ++r)
+    for (int a = 0; a < k; ++a) cells_per_arch[a] += cnt_all[(size_t)r * k + a];
   SC_TRY(gk_in.ensure(ctx, (size_t)annz + 1));
   SC_TRY(gk_out.ensure(ctx, (size_t)annz + 1));
   SC_TRY(gv_in.ensure(ctx, (size_t)annz + 1));
@@ -2550,8 +2607,9 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   g.row_begin = row_begin;
   g.row_end = row_end;
   g.prev = (t > 0 && r0_seed > 0) ? amin_cur.p : nullptr;
-  g.r0n = (t > 0 && r0_seed > 0) ? r0_seed : UPB_R0;
+  g.r0n = (t > 0 && r0_seed > 0) ? r0_seed : std::max(8, (UPB_R0 + ctx->world() - 1) / ctx->world());
   const long long nchunks = nchunks_cur;
+  const double* prune = bound_v.p;
   pstart();
   if ((int)ev_a.size() <= t) {
     cudaEvent_t ea, eb;
@@ -2568,9 +2626,21 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
       SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)(row_end - row_begin) * 32 + 255) / 256), 256, 0, row_begin, row_end,
                 KB.view(), cmax_v.p, cmax_l.p);
     SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
-              bound_v.p);
+              bound_v.p, bound_v.p);
+    if (ctx->world() > 1) {
+      // every rank evaluated the 64 / world largest-t2 candidates of each archetype among ITS cells; the smallest of the
+      // round-0 minima is the bound all of them prune with (one more k x 8-byte all-gather per step, instead of every
+      // rank evaluating 64 candidates per archetype on its own)
+      const int w = ctx->world();
+      SC_TRY(bound_all.ensure(ctx, (size_t)w * k + k));
+      SC_CUDA(ctx, cudaMemcpyAsync(bound_all.p + (size_t)ctx->rank() * k, bound_v.p, sizeof(double) * (size_t)k,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+      SC_TRY(exchange(bound_all.p, sizeof(double) * (size_t)k));
+      prune = bound_all.p + (size_t)w * k;
+      SC_LAUNCH(ctx, k_min_over_ranks, (k + 255) / 256, 256, 0, k, w, bound_all.p, bound_all.p + (size_t)w * k);
+    }
     SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
-              part_v.p, part_i.p, bound_v.p);
+              part_v.p, part_i.p, bound_v.p, prune);
   }
   if (n_hub > 0) {
     const int nloc = row_end - row_begin;
@@ -2605,7 +2675,7 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
   }
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
-  SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p,
+  SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p, prune,
             hub_slot.p, partial_dev);
   pstop(P_GEVAL);
   return SC_OK;

@@ -67,8 +67,8 @@ struct sc_fit {
   DBuf<unsigned> co_in, co_out;
   DBuf<int> c_cellv;
   DBuf<double> c_t2v;
-  DBuf<int> chunk_arch, part_i, hub_list;
-  DBuf<double> part_v, cmax_v, bound_v;
+  DBuf<int> chunk_arch, part_i, hub_list, arch_cnt_all;
+  DBuf<double> part_v, cmax_v, bound_v, bound_all;
   DBuf<int> cmax_l;
   DBuf<unsigned char> hub_flag;
   DBuf<unsigned long long> eval_cnt;
@@ -77,6 +77,8 @@ struct sc_fit {
   std::vector<cudaEvent_t> ev_a, ev_b, ev_h0, ev_h1;
   double hub_ms_total = 0.0, hub_bytes_total = 0.0;  // k_updateB_hub alone (incremental launches)
   long long hub_steps = 0, hub_launches_counted = 0, last_push_total = 0;
+  bool last_push_sync_free = false;
+  int k_maxrow = 0;  // longest row of this rank's columns of K
   double eval_ms_total = 0.0;
   long long eval_steps = 0;
   long long last_kb_nnz = 0;

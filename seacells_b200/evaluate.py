@@ -36,7 +36,7 @@ def compactness(ad, low_dim_embedding="X_pca", SEACells_label="SEACell", diffusi
     """evaluate.py:6-26: per metacell, the variance (ddof = 1) of every diffusion component over its cells, averaged
     over the components."""
     dc = _multiscale_space(ad, low_dim_embedding, 10, diffusion_components)
-    return pd.DataFrame(dc.join(ad.obs[SEACells_label]).groupby(SEACells_label).var().mean(1)).rename(
+    return pd.DataFrame(dc.join(ad.obs[SEACells_label]).groupby(SEACells_label).var().mean(axis=1)).rename(
         columns={0: "compactness"})
 
 
@@ -59,7 +59,8 @@ def separation(ad, low_dim_embedding="X_pca", nth_nbr=1, cluster=None, SEACells_
     metacells_nbrs.columns += 1
     if cluster is not None:
         clusters = ad.obs.groupby(SEACells_label)[cluster].agg(lambda x: x.value_counts().index[0])
-        nbr_clusters = pd.DataFrame(clusters.values[idx]).set_index(clusters.index)
+        nbr_clusters = pd.DataFrame(np.asarray(clusters.values, dtype=object)[idx]).set_index(clusters.index)  # (Arrow-backed strings
+        # of pandas 3 cannot be indexed with a 2-D array, which is what the reference does at evaluate.py:70)
         nbr_clusters.columns = metacells_nbrs.columns
         nbr_clusters = nbr_clusters.join(pd.DataFrame(clusters))
         clusters_match = nbr_clusters.eq(nbr_clusters[cluster], axis=0)

@@ -241,7 +241,7 @@ def test_evaluate_compactness_and_separation():
     ad.obs["celltype"] = rng.choice(["a", "b", "c"], size=n)
     df = pd.DataFrame(dc, index=ad.obs_names).join(ad.obs["SEACell"])
     comp = evaluate.compactness(ad, diffusion_components=dc)
-    np.testing.assert_allclose(comp["compactness"].values, df.groupby("SEACell").var().mean(1).values, rtol=1e-12)
+    np.testing.assert_allclose(comp["compactness"].values, df.groupby("SEACell").var().mean(axis=1).values, rtol=1e-12)
     cent = df.groupby("SEACell").mean()
     for nth in (1, 3):
         sep = evaluate.separation(ad, nth_nbr=nth, diffusion_components=dc)

@@ -191,14 +191,15 @@ def run_reference(args):
               f"outer iterations, T=50) of the oracle restatement of cpu.SEACellsCPU on a {n}-cell x 50-PC sample (k={k}) "
               f"of the workload; scipy sparse, each replica single-threaded as the reference's loop is; value = "
               f"replicas x cells / wall seconds")
-    # same-config pair (BASELINE config 1): ONE full 10k-cell fit per replica, untimed kernel construction
+    # same-config pair (BASELINE config 1): ONE full 10k-cell fit, alone on the box (the latency a user of the reference
+    # sees; its Frank-Wolfe loop is single-threaded scipy), kernel construction untimed as in the GPU arm
     same = None
     if not args.no_same_config:
-        c1_rep, c1_iters, c1_k = cpu_fit_replicas(C1_CELLS, min(procs, 8), 1)
+        c1_rep, c1_iters, c1_k = cpu_fit_replicas(C1_CELLS, 1, 1)
         same = {"config": f"config 1: synthetic {C1_CELLS} cells x 50 PCs, n_SEACells={c1_k}, full fit() "
-                          f"(initialize + {c1_iters} outer iterations)", "cpu_fit_s": c1_rep[0], "cpu_replicas": min(procs, 8),
-                "cpu_cells_per_s_one_fit": C1_CELLS / c1_rep[0],
-                "cpu_cells_per_s_all_replicas": min(procs, 8) * C1_CELLS / c1_rep[0], "kind": "port"}
+                          f"(initialize + {c1_iters} outer iterations)", "cpu_fit_s": c1_rep[0], "cores": 1,
+                "cpu_cells_per_s": C1_CELLS / c1_rep[0], "kind": "port",
+                "gpu_side": "`same_config.gpu_fit_s` of the default (`--impl ours`) line of the same run"}
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",

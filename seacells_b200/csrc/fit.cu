@@ -960,7 +960,7 @@ __global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restric
 // locality order was measured and dropped: 1.5 ms against 0.94 ms for this one at 1M cells - its warps walk separate
 // 32-cell blocks, the L1 hit rate of the t1 gathers fell from 70 % to 29 %, and the stages serialise behind barriers.)
 template <int R, int HUB_UNROLL>
-__global__ void __launch_bounds__(256, 2) k_updateB_hub(int row_begin, int row_end, int nh_pad,
+__global__ void __launch_bounds__(256, (HUB_UNROLL <= 2 ? 3 : 2)) k_updateB_hub(int row_begin, int row_end, int nh_pad,
                                                         const int* __restrict__ perm, RowLists KB,
                                                         const double* __restrict__ T1H, const double* __restrict__ T2H,
                                                         double* __restrict__ HH, int incremental, double c_old,
@@ -1899,12 +1899,23 @@ sc_fit::~sc_fit() {
   for (auto e : ev_b) cudaEventDestroy(e);
   for (auto e : ev_h0) cudaEventDestroy(e);
   for (auto e : ev_h1) cudaEventDestroy(e);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (stream2) {
+    cudaStreamSynchronize(stream2);
+    cudaStreamDestroy(stream2);
+  }
 }
 
 int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   ctx = c;
   profile = std::getenv("SC_PROFILE") != nullptr;
   fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
+  overlap_hub = std::getenv("SC_NO_OVERLAP") == nullptr;
+  if (const char* e = std::getenv("SC_HUB_U")) hub_u = atoi(e) == 2 ? 2 : 4;  // cells in flight per warp of the hub kernel
+  SC_CUDA(ctx, cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+  SC_CUDA(ctx, cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  SC_CUDA(ctx, cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   resum_A = std::getenv("SC_FIT_RESUM_A") != nullptr;
   if (const char* e = std::getenv("SC_HUB_MAX")) hub_cap = std::max(0, std::min(HUB_MAX, atoi(e)));
   if (const char* e = std::getenv("SC_R0_SEED")) r0_seed = std::max(0, std::min(UPB_R0, atoi(e)));
@@ -2234,11 +2245,14 @@ static void swap_lists(RowListsBuf& a, RowListsBuf& b) {
 
 // K B_t from K B_{t-1} and the cells chosen at step t-1 (amin_cur, written by k_updateB_step):
 //   K B_t = (1 - gamma_{t-1}) K B_{t-1} + gamma_{t-1} K E_{t-1},   gamma_0 = 1 (B was reset to E_0)
-int sc_fit::advance_KB(int t) {
+int sc_fit::advance_KB_delta() {
   pstart();
   PushSrc src{k, amin_cur.p, nullptr, nullptr};
   SC_TRY(push_product(src, false, DKB));
   pstop(P_SPGEMM_Y);
+  return SC_OK;
+}
+int sc_fit::advance_KB_merge(int t) {
   pstart();
   if (t == 1) {
     swap_lists(KB, DKB);  // gamma_0 = 1
@@ -2578,6 +2592,7 @@ int sc_fit::update_B_begin() {
 int sc_fit::update_B_eval(int t, double* partial_dev) {
   if (!in_update_B) SC_FAIL(ctx, SC_ERR_STATE, "update_B_eval outside update_B_begin/end");
   if (t < 0 || t >= T) SC_FAIL(ctx, SC_ERR_ARG, "update_B_eval: bad step");
+  bool hub_async = false;
   // K B for the current B (cpu.py:486), this rank's rows, first-occurrence order (the rows are only walked here):
   // evaluated from B at the first step, then advanced by the step's rank-k change (see k_kb_merge)
   if (t == 0) {
@@ -2585,7 +2600,15 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   } else if (fresh_kb) {
     SC_TRY(compute_KB(false));
   } else {
-    SC_TRY(advance_KB(t));
+    SC_TRY(advance_KB_delta());
+    if (overlap_hub && t >= 2 && n_hub > 0) {  // fork: the hub gradient needs the delta rows only
+      SC_CUDA(ctx, cudaEventRecord(ev_fork, ctx->stream));
+      SC_CUDA(ctx, cudaStreamWaitEvent(stream2, ev_fork, 0));
+      SC_TRY(launch_hub(t, stream2, partial_dev));
+      SC_CUDA(ctx, cudaEventRecord(ev_join, stream2));
+      hub_async = true;
+    }
+    SC_TRY(advance_KB_merge(t));
   }
   UpdBArgs g;
   g.n = n;
@@ -2642,42 +2665,64 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
               part_v.p, part_i.p, bound_v.p, prune);
   }
-  if (n_hub > 0) {
-    const int nloc = row_end - row_begin;
-    const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
-    // steps 0 and 1 evaluate the product in full (K B from the previous B, then K E_0); later steps advance it
-    const bool inc = !fresh_kb && t >= 2;
-    const double gamma = inc ? 2.0 / ((double)(t - 1) + 2.0) : 0.0;
-    const RowLists hub_rows = inc ? DKB.view() : KB.view();
-    if ((int)ev_h0.size() <= t) {
-      cudaEvent_t ea, eb;
-      SC_CUDA(ctx, cudaEventCreate(&ea));
-      SC_CUDA(ctx, cudaEventCreate(&eb));
-      ev_h0.push_back(ea);
-      ev_h1.push_back(eb);
-    }
-    if (inc) {  // algorithmic bytes of this launch: HH read + write and t2, 8 B each per (cell, hub), + the delta rows
-      hub_bytes_total += 24.0 * (double)nloc * n_hub + 12.0 * (double)last_push_total;
-      hub_launches_counted++;
-    }
-    SC_CUDA(ctx, cudaEventRecord(ev_h0[t], ctx->stream));
-#define SC_HUB_LAUNCH(RR)                                                                                              \
-  SC_LAUNCH(ctx, (k_updateB_hub<RR, (RR <= 2 ? 4 : 2)>), nctas, 256, 0, row_begin, row_end, n_hub_pad, perm.p, hub_rows, \
-            T1H.p, T2H.p, HH.p, inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p)
-    if (nctas > 0) switch (n_hub_pad / 32) {
+  if (n_hub > 0 && !hub_async) SC_TRY(launch_hub(t, ctx->stream, partial_dev));
+  SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
+  SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p, prune,
+            hub_slot.p, partial_dev);
+  if (hub_async) SC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_join, 0));  // the hub archetypes' partials are in
+  pstop(P_GEVAL);
+  return SC_OK;
+}
+
+// The cell-major gradient of the hub archetypes for step t on `stream` (see k_updateB_hub).  From step 2 on it depends on
+// the step's delta rows only - not on the merged K B - so update_B_eval runs it on a second stream next to the merge and
+// the two rounds of k_updateB_eval: both chains are latency bound and share the SMs well.
+int sc_fit::launch_hub(int t, cudaStream_t stream, double* partial_dev) {
+  const int nloc = row_end - row_begin;
+  const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
+  // steps 0 and 1 evaluate the product in full (K B from the previous B, then K E_0); later steps advance it
+  const bool inc = !fresh_kb && t >= 2;
+  const double gamma = inc ? 2.0 / ((double)(t - 1) + 2.0) : 0.0;
+  const RowLists hub_rows = inc ? DKB.view() : KB.view();
+  if ((int)ev_h0.size() <= t) {
+    cudaEvent_t ea, eb;
+    SC_CUDA(ctx, cudaEventCreate(&ea));
+    SC_CUDA(ctx, cudaEventCreate(&eb));
+    ev_h0.push_back(ea);
+    ev_h1.push_back(eb);
+  }
+  if (inc) {  // algorithmic bytes of this launch: HH read + write and t2, 8 B each per (cell, hub), + the delta rows
+    hub_bytes_total += 24.0 * (double)nloc * n_hub + 12.0 * (double)last_push_total;
+    hub_launches_counted++;
+  }
+  SC_CUDA(ctx, cudaEventRecord(ev_h0[t], stream));
+#define SC_HUB_LAUNCH_U(RR, UU)                                                                                        \
+  do {                                                                                                                 \
+    k_updateB_hub<RR, UU><<<nctas, 256, 0, stream>>>(row_begin, row_end, n_hub_pad, perm.p, hub_rows, T1H.p, T2H.p, HH.p, \
+                                                     inc ? 1 : 0, 1.0 - gamma, gamma, hub_part.p);                      \
+    ctx->launches++;                                                                                                   \
+    SC_CUDA(ctx, cudaGetLastError());                                                                                  \
+  } while (0)
+#define SC_HUB_LAUNCH(RR)          \
+  do {                             \
+    if (hub_u == 4 && (RR) <= 2) { \
+      SC_HUB_LAUNCH_U(RR, 4);      \
+    } else {                       \
+      SC_HUB_LAUNCH_U(RR, 2);      \
+    }                              \
+  } while (0)
+  if (nctas > 0) switch (n_hub_pad / 32) {
       case 1: SC_HUB_LAUNCH(1); break;
       case 2: SC_HUB_LAUNCH(2); break;
       case 3: SC_HUB_LAUNCH(3); break;
       default: SC_HUB_LAUNCH(4); break;
     }
+#undef SC_HUB_LAUNCH_U
 #undef SC_HUB_LAUNCH
-    SC_CUDA(ctx, cudaEventRecord(ev_h1[t], ctx->stream));
-    SC_LAUNCH(ctx, k_updateB_hub_reduce, n_hub, 256, 0, nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
-  }
-  SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));
-  SC_LAUNCH(ctx, k_updateB_local, k, 256, 0, g, row_begin, row_end, chunk_ptr.p, part_v.p, part_i.p, bound_v.p, prune,
-            hub_slot.p, partial_dev);
-  pstop(P_GEVAL);
+  SC_CUDA(ctx, cudaEventRecord(ev_h1[t], stream));
+  k_updateB_hub_reduce<<<n_hub, 256, 0, stream>>>(nctas, n_hub_pad, hub_ids.p, hub_part.p, partial_dev);
+  ctx->launches++;
+  SC_CUDA(ctx, cudaGetLastError());
   return SC_OK;
 }
 

@@ -54,6 +54,10 @@ struct sc_fit {
   // 3.97 s), m = 64 changes nothing - the previous winner is almost always among the 64 anyway.  Off by default.
   int r0_seed = 0;
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
+  cudaStream_t stream2 = nullptr;  // the hub gradient of a Frank-Wolfe step runs here, next to the merge + chunk kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int hub_u = 4;
+  bool overlap_hub = true;         // SC_NO_OVERLAP=1: everything on one stream
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step
   DBuf<long long> b_off;
@@ -111,7 +115,9 @@ struct sc_fit {
   int push_product(const struct PushSrc& src, bool has_dups, RowListsBuf& Z);
   int allgather_rows(const RowLists& L, const unsigned* keep, RowListsBuf& G);
   int compute_KB(bool with_support);
-  int advance_KB(int t);
+  int advance_KB_delta();
+  int advance_KB_merge(int t);
+  int launch_hub(int t, cudaStream_t stream, double* partial_dev);
   int build_perm();
   int update_B_begin();
   int update_B_eval(int t, double* partial_dev);

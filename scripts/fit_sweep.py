@@ -12,7 +12,7 @@ km = build_kernel(X, 15)
 arch = synth_archetypes(n, k); A0 = normalize(synth_assignments(n, k), axis=0, norm="l1")
 for cfg in sys.argv[2:] or [""]:
     sw = dict(kv.split("=") for kv in cfg.split(",") if kv)
-    for key in ("SC_R0_SEED", "SC_HUB_MAX", "SC_FIT_FRESH_KB", "SC_FIT_RESUM_A", "SC_NO_OVERLAP"): os.environ.pop(key, None)
+    for key in ("SC_R0_SEED", "SC_HUB_MAX", "SC_FIT_FRESH_KB", "SC_FIT_RESUM_A", "SC_NO_OVERLAP", "SC_HUB_U"): os.environ.pop(key, None)
     os.environ.update(sw)
     eng = FitEngine(n, k); eng.set_kernel(km)
     ts = []

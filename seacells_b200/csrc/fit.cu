@@ -1912,7 +1912,7 @@ int sc_fit::init(sc_ctx* c, int n_, int k_, int T_) {
   profile = std::getenv("SC_PROFILE") != nullptr;
   fresh_kb = std::getenv("SC_FIT_FRESH_KB") != nullptr;
   overlap_hub = std::getenv("SC_NO_OVERLAP") == nullptr;
-  if (const char* e = std::getenv("SC_HUB_U")) hub_u = atoi(e) == 2 ? 2 : 4;  // cells in flight per warp of the hub kernel
+  if (const char* e = std::getenv("SC_HUB_U")) hub_u = atoi(e) == 4 ? 4 : 2;
   SC_CUDA(ctx, cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
   SC_CUDA(ctx, cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   SC_CUDA(ctx, cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));

@@ -56,7 +56,7 @@ struct sc_fit {
   int hub_cap = 64;       // archetypes evaluated by the dense hub block at most (<= HUB_MAX; SC_HUB_MAX overrides)
   cudaStream_t stream2 = nullptr;  // the hub gradient of a Frank-Wolfe step runs here, next to the merge + chunk kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int hub_u = 4;
+  int hub_u = 2;   // cells in flight per warp of the hub kernel (SC_HUB_U=4: 125 registers, 2 CTAs per SM; 2: 80 registers, 3 CTAs)
   bool overlap_hub = true;         // SC_NO_OVERLAP=1: everything on one stream
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step

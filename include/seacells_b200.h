@@ -177,7 +177,9 @@ int sc_fit_soft_assignments(sc_fit* fit, int top, int32_t* idx, double* w);
  * not produced by the merge, both rounds of k_updateB_eval, k_updateB_hub and its reduction, the locality permutation at
  * step 0), [7] nnz of the last K*B row lists, [8] steps timed and [9] summed CUDA-event ns of k_updateB_hub alone,
  * [10] its algorithmic bytes per launch (24 B x cells x hubs + 12 B x delta entries), [11] 1024-candidate chunks of the last
- * _updateB that were discarded unread by the sorted-list bound and [12] chunk CTAs launched (all steps).  out: 16 values. */
+ * _updateB that were discarded unread by the sorted-list bound and [12] chunk CTAs launched (all steps), [13] Frank-Wolfe
+ * steps of the last _updateA whose zero scan went past archetype 31 and [14] the 32-wide batches they scanned.
+ * out: 16 values. */
 int sc_fit_stats(sc_fit* fit, long long* out16);
 /* with SC_PROFILE=1 in the environment: accumulated wall seconds per stage (synchronising; development aid).
  * [0] B-by-cell [1] M*B [2] M*(M*B) [3] t1=B^T K B [4] _updateA shared-memory path [5] _updateA generic path

@@ -21,5 +21,5 @@ for cfg in sys.argv[2:] or [""]:
         s0 = eng.stats(); t = time.time(); rss, it, conv, _ = eng.run(max_iter=100, min_iter=10); eng.ctx.sync(); ts.append(time.time() - t); s1 = eng.stats()
     grp = (s1["updB_eval_ns_total"] - s0["updB_eval_ns_total"]) / max(1, s1["updB_steps_timed"] - s0["updB_steps_timed"]) / 1e6
     hub = (s1["hub_ns_total"] - s0["hub_ns_total"]) / max(1, s1["hub_steps_timed"] - s0["hub_steps_timed"]) / 1e6
-    print(f"{cfg or 'default':28s} fit s {['%.3f' % x for x in ts]} iters {it} rss_last {rss[-1]!r} group ms/step {grp:.3f} hub ms/step {hub:.3f} hub bytes/launch {s1['hub_bytes_per_launch']/1e9:.3f} GB evaluated {s1['gradients_evaluated_last_update_B']/1e6:.0f}M t2nnz {s1['t2_nnz_last_update_B']/1e6:.0f}M hubs {s1['hub_archetypes_last_update_B']} chunks pruned/launched {s1['chunks_pruned_unread_last_update_B']}/{s1['chunk_launches_last_update_B']}", flush=True)
+    print(f"{cfg or 'default':28s} fit s {['%.3f' % x for x in ts]} iters {it} rss_last {rss[-1]!r} group ms/step {grp:.3f} hub ms/step {hub:.3f} hub bytes/launch {s1['hub_bytes_per_launch']/1e9:.3f} GB evaluated {s1['gradients_evaluated_last_update_B']/1e6:.0f}M t2nnz {s1['t2_nnz_last_update_B']/1e6:.0f}M hubs {s1['hub_archetypes_last_update_B']} chunks pruned/launched {s1['chunks_pruned_unread_last_update_B']}/{s1['chunk_launches_last_update_B']} updA long scans {s1['updA_long_zero_scans']} batches {s1['updA_long_zero_scan_batches']}", flush=True)
     eng.close()

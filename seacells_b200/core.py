@@ -295,7 +295,8 @@ class FitEngine:
                 "gradients_evaluated_last_update_B": int(out[4]), "updB_steps_timed": int(out[5]),
                 "updB_eval_ns_total": int(out[6]), "kb_nnz_last": int(out[7]), "hub_steps_timed": int(out[8]),
                 "hub_ns_total": int(out[9]), "hub_bytes_per_launch": int(out[10]),
-                "chunks_pruned_unread_last_update_B": int(out[11]), "chunk_launches_last_update_B": int(out[12])}
+                "chunks_pruned_unread_last_update_B": int(out[11]), "chunk_launches_last_update_B": int(out[12]),
+                "updA_long_zero_scans": int(out[13]), "updA_long_zero_scan_batches": int(out[14])}
 
     def shard(self):
         """Cells [begin, end) this rank owns (the whole range on one GPU)."""

@@ -607,7 +607,9 @@ int sc_fit_stats(sc_fit* fit, long long* out4) {
   out4[10] = fit->hub_launches_counted ? (long long)(fit->hub_bytes_total / (double)fit->hub_launches_counted) : 0;
   out4[11] = fit->last_pruned_chunks;
   out4[12] = fit->last_chunk_launches;
-  for (int i = 13; i < 16; ++i) out4[i] = 0;
+  out4[13] = (long long)fit->last_updA_diag[0];
+  out4[14] = (long long)fit->last_updA_diag[1];
+  out4[15] = 0;
   return SC_OK;
 }
 int sc_fit_profile(sc_fit* fit, double* out16) {

@@ -372,6 +372,7 @@ struct UpdAArgs {
   int* trace;  // [T * n] or null
   int* slow_list;
   int* slow_cnt;
+  unsigned long long* diag;  // [0] Frank-Wolfe steps whose zero scan had to go past archetype 31, [1] 32-wide batches they scanned
 };
 
 // binary search for `key` in a sorted list; returns value or 0
@@ -525,8 +526,15 @@ __global__ void __launch_bounds__(FWA_WARPS * 32) k_updateA_fast(UpdAArgs g) {
         // dense-column rule: first exact zero, archetypes ascending; the first 32 come from the running product
         const double Gz = (lane < k) ? 2.0 * (Hz[lane] - list_lookup(ck, ct2, nc, lane)) : FW_INF;
         const unsigned z = __ballot_sync(0xffffffffu, Gz == 0.0);
-        if (z) chosen = __ffs(z) - 1;
-        else chosen = fwA_zero_scan(k, t1T, sid, sa, nslots, ck, ct2, nc, lane, 32, Gz, lane);
+        if (z) {
+          chosen = __ffs(z) - 1;
+        } else {
+          chosen = fwA_zero_scan(k, t1T, sid, sa, nslots, ck, ct2, nc, lane, 32, Gz, lane);
+          if (lane == 0 && g.diag) {
+            atomicAdd(g.diag, 1ull);
+            atomicAdd(g.diag + 1, (unsigned long long)((chosen >= 32 ? chosen - 32 : k) / 32 + 1));
+          }
+        }
       }
       const double gamma = fw_gamma(t);
       int pos = -1;
@@ -912,10 +920,6 @@ struct UpdBArgs {
 constexpr int UPB_CHUNK = 1024;  // candidates per CTA
 __device__ __forceinline__ void block_argmin_256(double& v, int& i, double* sg, int* si);
 
-__global__ void k_cand_counts(int k, const long long* __restrict__ c_ptr, long long* __restrict__ out) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a < k) out[a] = c_ptr[a + 1] - c_ptr[a];
-}
 __global__ void k_chunk_count(int k, const long long* __restrict__ c_ptr, const int* __restrict__ hub_slot,
                               int* __restrict__ nch) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -938,14 +942,71 @@ __global__ void k_hub_t1(int k, int nh, int nh_pad, const int* __restrict__ hub_
   if (l >= k) return;
   T1H[(size_t)l * nh_pad + s] = (s < nh) ? t1[(size_t)hub_ids[s] * k + l] : 0.0;
 }
-__global__ void k_hub_t2(int nh, int nh_pad, int row_begin, const int* __restrict__ hub_ids,
-                         const long long* __restrict__ c_ptr, const int* __restrict__ c_cell,
-                         const double* __restrict__ c_t2, double* __restrict__ T2H) {
-  const int s = blockIdx.y;
-  const int a = hub_ids[s];
-  for (long long e = c_ptr[a] + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < c_ptr[a + 1];
-       e += (long long)gridDim.x * blockDim.x)
-    T2H[(size_t)(c_cell[e] - row_begin) * nh_pad + s] = c_t2[e];
+// The hub archetypes' share of t2 = K A^T is dense (every cell is a candidate), so it is not pushed through the sparse
+// row products and the candidate sort at all: the hub slots of A are split off into a dense [cells x padded hubs] matrix
+// AH and t2[:, hubs] = M (M AH) is two CSR x dense products with 8 x nh_pad-byte rows.  Same products, same order of
+// the sums as the sparse path (which adds the same non-zero terms in ascending column order; the dense rows add exact
+// zeros in between), multiply and add rounded separately: the values are bitwise those of the sparse rows.
+__global__ void k_split_slots(int n, int S, int nh_pad, const int* __restrict__ hub_slot, const int* __restrict__ a_idx,
+                              const double* __restrict__ a_val, const int* __restrict__ a_cnt,
+                              int* __restrict__ o_key, double* __restrict__ o_val, int* __restrict__ o_len,
+                              double* __restrict__ AH) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int cnt = a_cnt[j];
+  int w = 0;
+  for (int s0 = 0; s0 < cnt; s0 += 32) {
+    const int s = s0 + lane;
+    int a = -1, hs = -1;
+    double v = 0.0;
+    if (s < cnt) {
+      a = a_idx[(size_t)j * S + s];
+      v = a_val[(size_t)j * S + s];
+      hs = hub_slot[a];
+      if (hs >= 0) AH[(size_t)j * nh_pad + hs] = v;
+    }
+    const bool keep = a >= 0 && hs < 0;
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = w + __popc(ball & ((1u << lane) - 1u));
+      o_key[(size_t)j * S + pos] = a;
+      o_val[(size_t)j * S + pos] = v;
+    }
+    w += __popc(ball);
+  }
+  if (lane == 0) o_len[j] = w;
+}
+// Y[i - out0, :] = sum_q M[i, q] X[q, :] for rows [r0, r1), nh_pad = 32 R columns; lane l owns columns l, l + 32, ...
+template <int R>
+__global__ void __launch_bounds__(256)
+k_spmm_hubcols(int r0, int r1, int out0, int nh_pad, const int* __restrict__ indptr, const int* __restrict__ indices,
+               const double* __restrict__ data, const double* __restrict__ X, double* __restrict__ Y) {
+  const int i = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= r1) return;
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+  const int s0 = indptr[i], s1 = indptr[i + 1];
+  for (int base = s0; base < s1; base += 32) {
+    int q = 0;
+    double m = 0.0;
+    if (base + lane < s1) {
+      q = indices[base + lane];
+      m = data[base + lane];
+    }
+    const int cnt = min(32, s1 - base);
+#pragma unroll 4
+    for (int e = 0; e < cnt; ++e) {
+      const int qq = __shfl_sync(0xffffffffu, q, e);
+      const double mm = __shfl_sync(0xffffffffu, m, e);
+      const double* __restrict__ xr = X + (size_t)qq * nh_pad + lane;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = __dadd_rn(acc[r], __dmul_rn(mm, __ldg(xr + r * 32)));
+    }
+  }
+  double* yr = Y + (size_t)(i - out0) * nh_pad + lane;
+#pragma unroll
+  for (int r = 0; r < R; ++r) yr[r * 32] = acc[r];
 }
 
 // out[cta][slot][4] = {candidate min G, cell, non-candidate min G, cell} over the CTA's cells
@@ -2344,6 +2405,9 @@ int sc_fit::update_A(double l2, int* trace_dev) {
   g.trace = trace_dev;
   g.slow_list = slow_list.p;
   g.slow_cnt = slow_cnt.p;
+  SC_TRY(updA_diag.ensure(ctx, 2));
+  SC_CUDA(ctx, cudaMemsetAsync(updA_diag.p, 0, sizeof(unsigned long long) * 2, ctx->stream));
+  g.diag = updA_diag.p;
   SC_CUDA(ctx, cudaMemsetAsync(slow_cnt.p, 0, sizeof(int), ctx->stream));
   int nslow = 0;
   pstart();
@@ -2352,6 +2416,8 @@ int sc_fit::update_A(double l2, int* trace_dev) {
     if (resum_A) SC_LAUNCH(ctx, k_updateA_fast<true>, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
     else SC_LAUNCH(ctx, k_updateA_fast<false>, grid, FWA_WARPS * 32, FWA_PER_WARP * FWA_WARPS, g);
     SC_CUDA(ctx, cudaMemcpyAsync(&nslow, slow_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyAsync(last_updA_diag, updA_diag.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   } else {
     // the -l2*A term can make entries outside the support of t2 negative: every cell takes the generic path
@@ -2479,9 +2545,55 @@ int sc_fit::update_B_begin() {
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
   }
   pstop(P_GRAM);
+  // ---- hub block of this call: the archetypes that carry weight from more than 1/16 of all cells (at most hub_cap of
+  // them, the most populated first).  Their gradient is evaluated cell-major by k_updateB_hub and their share of t2 is
+  // dense; the choice depends on A alone, which every rank holds in full.
+  {
+    std::vector<std::pair<long long, int>> big;
+    const long long thr = std::max<long long>(32, n / 16);
+    for (int a = 0; a < k; ++a)
+      if (cells_per_arch[a] > thr) big.push_back({-(long long)cells_per_arch[a], a});
+    std::sort(big.begin(), big.end());
+    if ((int)big.size() > hub_cap) big.resize(hub_cap);
+    std::vector<int> ids, slot(k, -1);
+    for (auto& b : big) ids.push_back(b.second);
+    std::sort(ids.begin(), ids.end());
+    for (size_t q = 0; q < ids.size(); ++q) slot[ids[q]] = (int)q;
+    n_hub = (int)ids.size();
+    n_hub_pad = ((n_hub + 31) / 32) * 32;
+    SC_TRY(hub_ids.ensure(ctx, (size_t)HUB_MAX));
+    SC_TRY(hub_slot.ensure(ctx, (size_t)k));
+    if (n_hub) SC_CUDA(ctx, cudaMemcpyAsync(hub_ids.p, ids.data(), sizeof(int) * n_hub, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyAsync(hub_slot.p, slot.data(), sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    last_hub_block = n_hub;
+  }
   // ---- t2 = K A^T as per-cell rows, then as per-archetype candidate lists
   pstart();
   RowLists Al{slot_ptr_n.p, a_cnt[cur].p, a_idx[cur].p, a_val[cur].p};
+  if (n_hub > 0) {
+    const int nloc = row_end - row_begin;
+    SC_TRY(ah_len.ensure(ctx, (size_t)n + 1));
+    SC_TRY(ah_key.ensure(ctx, (size_t)n * S));
+    SC_TRY(ah_val.ensure(ctx, (size_t)n * S));
+    SC_TRY(AH.ensure(ctx, (size_t)n * n_hub_pad));
+    SC_TRY(YH.ensure(ctx, (size_t)n * n_hub_pad));
+    SC_TRY(T2H.ensure(ctx, (size_t)std::max(nloc, 1) * n_hub_pad));
+    SC_CUDA(ctx, cudaMemsetAsync(AH.p, 0, sizeof(double) * (size_t)n * n_hub_pad, ctx->stream));
+    SC_LAUNCH(ctx, k_split_slots, (unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, n, S, n_hub_pad, hub_slot.p, a_idx[cur].p,
+              a_val[cur].p, a_cnt[cur].p, ah_key.p, ah_val.p, ah_len.p, AH.p);
+    Al = RowLists{slot_ptr_n.p, ah_len.p, ah_key.p, ah_val.p};  // A without its hub rows
+#define SC_HUBCOLS(RR, A0, A1, OUT0, XX, YY)                                                                            \
+  SC_LAUNCH(ctx, k_spmm_hubcols<RR>, (unsigned)(((size_t)((A1) - (A0)) * 32 + 255) / 256), 256, 0, A0, A1, OUT0, n_hub_pad, \
+            m_ptr.p, m_col.p, m_val.p, XX, YY)
+    switch (n_hub_pad / 32) {
+      case 1: SC_HUBCOLS(1, 0, n, 0, AH.p, YH.p); if (nloc > 0) SC_HUBCOLS(1, row_begin, row_end, row_begin, YH.p, T2H.p); break;
+      case 2: SC_HUBCOLS(2, 0, n, 0, AH.p, YH.p); if (nloc > 0) SC_HUBCOLS(2, row_begin, row_end, row_begin, YH.p, T2H.p); break;
+      case 3: SC_HUBCOLS(3, 0, n, 0, AH.p, YH.p); if (nloc > 0) SC_HUBCOLS(3, row_begin, row_end, row_begin, YH.p, T2H.p); break;
+      default: SC_HUBCOLS(4, 0, n, 0, AH.p, YH.p); if (nloc > 0) SC_HUBCOLS(4, row_begin, row_end, row_begin, YH.p, T2H.p); break;
+    }
+#undef SC_HUBCOLS
+  }
   // rows in first-occurrence order (no compaction, no sort): the values do not depend on the order inside a row of the
   // right-hand side (a key occurs once per row), and the candidate lists are ordered by the radix sort below
   if (ctx->world() == 1) {
@@ -2504,7 +2616,7 @@ int sc_fit::update_B_begin() {
     SC_CUDA(ctx, cudaMemcpyAsync(&cnnz, t_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (cnnz >= (1ll << 32)) SC_FAIL(ctx, SC_ERR_CAPACITY, "update_B: more than 2^32 candidate pairs");
-    last_t2_nnz = cnnz;
+    last_t2_nnz = cnnz + (long long)n_hub * (row_end - row_begin);  // sparse candidates + the dense hub columns
     SC_TRY(ck_in.ensure(ctx, (size_t)cnnz + 1));
     SC_TRY(ck_out.ensure(ctx, (size_t)cnnz + 1));
     SC_TRY(co_in.ensure(ctx, (size_t)cnnz + 1));
@@ -2521,50 +2633,13 @@ int sc_fit::update_B_begin() {
     SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
               c_t2.p);
   }
-  // hub block: archetypes whose candidate list covers more than a quarter of all cells (at most hub_cap of them).  The
-  // choice is made on the candidate counts summed over the ranks, so every rank routes an archetype through the same
-  // kernel and a column's gradients are the same numbers however the cells are sharded.
-  {
+  if (n_hub > 0) {  // hub block (chosen above): slices of t1 by hub column, running product, per-CTA partial results
     const int nloc = row_end - row_begin;
-    const int w = ctx->world();
-    SC_TRY(cand_cnt.ensure(ctx, (size_t)w * k));
-    SC_LAUNCH(ctx, k_cand_counts, (k + 255) / 256, 256, 0, k, c_ptr.p, cand_cnt.p + (size_t)ctx->rank() * k);
-    SC_TRY(exchange(cand_cnt.p, sizeof(long long) * (size_t)k));
-    std::vector<long long> hall((size_t)w * k), hc((size_t)k, 0);
-    SC_CUDA(ctx, cudaMemcpyAsync(hall.data(), cand_cnt.p, sizeof(long long) * hall.size(), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int r = 0; r < w; ++r)
-      for (int a = 0; a < k; ++a) hc[a] += hall[(size_t)r * k + a];
-    std::vector<std::pair<long long, int>> big;
-    const long long thr = std::max<long long>(4096, n / 4);
-    for (int a = 0; a < k; ++a)
-      if (hc[a] > thr) big.push_back({-hc[a], a});
-    std::sort(big.begin(), big.end());
-    if ((int)big.size() > hub_cap) big.resize(hub_cap);
-    std::vector<int> ids, slot(k, -1);
-    for (auto& b : big) ids.push_back(b.second);
-    std::sort(ids.begin(), ids.end());
-    for (size_t q = 0; q < ids.size(); ++q) slot[ids[q]] = (int)q;
-    n_hub = (int)ids.size();
-    n_hub_pad = ((n_hub + 31) / 32) * 32;
-    SC_TRY(hub_ids.ensure(ctx, (size_t)HUB_MAX));
-    SC_TRY(hub_slot.ensure(ctx, (size_t)k));
-    if (n_hub) SC_CUDA(ctx, cudaMemcpyAsync(hub_ids.p, ids.data(), sizeof(int) * n_hub, cudaMemcpyHostToDevice, ctx->stream));
-    SC_CUDA(ctx, cudaMemcpyAsync(hub_slot.p, slot.data(), sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_hub) {
-      const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
-      SC_TRY(T1H.ensure(ctx, (size_t)k * n_hub_pad));
-      SC_TRY(T2H.ensure(ctx, (size_t)nloc * n_hub_pad));
-      SC_TRY(HH.ensure(ctx, (size_t)nloc * n_hub_pad));
-      SC_TRY(hub_part.ensure(ctx, (size_t)nctas * n_hub_pad * 4));
-      SC_LAUNCH(ctx, k_hub_t1, dim3((k + 255) / 256, n_hub_pad), 256, 0, k, n_hub, n_hub_pad, hub_ids.p, t1B.p, T1H.p);
-      SC_CUDA(ctx, cudaMemsetAsync(T2H.p, 0, sizeof(double) * (size_t)nloc * n_hub_pad, ctx->stream));
-      SC_LAUNCH(ctx, k_hub_t2, dim3(296, n_hub), 256, 0, n_hub, n_hub_pad, row_begin, hub_ids.p, c_ptr.p, c_cell.p,
-                c_t2.p, T2H.p);
-    }
-    last_hub_block = n_hub;
+    const int nctas = (nloc + HUB_CELLS_PER_CTA - 1) / HUB_CELLS_PER_CTA;
+    SC_TRY(T1H.ensure(ctx, (size_t)k * n_hub_pad));
+    SC_TRY(HH.ensure(ctx, (size_t)std::max(nloc, 1) * n_hub_pad));
+    SC_TRY(hub_part.ensure(ctx, (size_t)std::max(nctas, 1) * n_hub_pad * 4));
+    SC_LAUNCH(ctx, k_hub_t1, dim3((k + 255) / 256, n_hub_pad), 256, 0, k, n_hub, n_hub_pad, hub_ids.p, t1B.p, T1H.p);
   }
   // chunk table: archetypes with long candidate lists are spread over many CTAs
   SC_TRY(chunk_ptr.ensure(ctx, (size_t)k + 1));

@@ -16,7 +16,8 @@ struct sc_fit {
   DBuf<int> hub_ids, hub_slot, gram_hubof, perm;
   DBuf<unsigned long long> pk_in, pk_out;
   DBuf<double> gram_tiles;
-  DBuf<double> T1H, T2H, HH, hub_part;  // HH: (K B t1)[cell, hubs], advanced step by step
+  DBuf<double> T1H, T2H, HH, hub_part, AH, YH, ah_val;  // AH: hub slots of A, dense; YH = M AH; ah_*: A without them
+  DBuf<int> ah_len, ah_key;  // HH: (K B t1)[cell, hubs], advanced step by step
   int n_hub = 0, n_hub_pad = 0, last_hub_block = 0;
   DBuf<double> part_out;  // [k][4] per-archetype partial result of one Frank-Wolfe step of _updateB on this rank
   // kernel matrix M
@@ -75,7 +76,8 @@ struct sc_fit {
   DBuf<double> part_v, cmax_v, bound_v, bound_all;
   DBuf<int> cmax_l;
   DBuf<unsigned char> hub_flag;
-  DBuf<unsigned long long> eval_cnt;
+  DBuf<unsigned long long> eval_cnt, updA_diag;
+  unsigned long long last_updA_diag[2] = {0, 0};
   long long last_evaluated = 0, last_pruned_chunks = 0, last_chunk_launches = 0;
   // CUDA-event timing of the dominant kernel (k_updateB_eval, both rounds of one Frank-Wolfe step), always on
   std::vector<cudaEvent_t> ev_a, ev_b, ev_h0, ev_h1;

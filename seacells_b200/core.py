@@ -39,7 +39,8 @@ class KernelMatrix:
 
     def close(self):
         if self.h is not None:
-            self.ctx.lib.sc_kernel_free(self.h)
+            if getattr(self.ctx, "h", None):  # a handle must not outlive its context's stream
+                self.ctx.lib.sc_kernel_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -314,7 +315,8 @@ class FitEngine:
 
     def close(self):
         if getattr(self, "h", None) is not None:
-            self.ctx.lib.sc_fit_destroy(self.h)
+            if getattr(self.ctx, "h", None):  # the context is gone (closed first): its stream no longer exists
+                self.ctx.lib.sc_fit_destroy(self.h)
             self.h = None
 
     def __del__(self):

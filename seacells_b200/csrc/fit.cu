@@ -2545,12 +2545,12 @@ int sc_fit::update_B_begin() {
     SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
   }
   pstop(P_GRAM);
-  // ---- hub block of this call: the archetypes that carry weight from more than 1/16 of all cells (at most hub_cap of
+  // ---- hub block of this call: the archetypes that carry weight from more than 1/64 of all cells (at most hub_cap of
   // them, the most populated first).  Their gradient is evaluated cell-major by k_updateB_hub and their share of t2 is
   // dense; the choice depends on A alone, which every rank holds in full.
   {
     std::vector<std::pair<long long, int>> big;
-    const long long thr = std::max<long long>(32, n / 16);
+    const long long thr = std::max<long long>(32, n / 64);
     for (int a = 0; a < k; ++a)
       if (cells_per_arch[a] > thr) big.push_back({-(long long)cells_per_arch[a], a});
     std::sort(big.begin(), big.end());
@@ -2630,8 +2630,9 @@ int sc_fit::update_B_begin() {
               co_in.p, c_cellv.p, c_t2v.p);
     SC_TRY(sc_sort_pairs_u64_u32(ctx, ck_in.p, ck_out.p, co_in.p, co_out.p, (size_t)cnnz, 32 + kbits, tmp));
     SC_LAUNCH(ctx, k_row_bounds, (k + 256) / 256, 256, 0, k, ck_out.p, cnnz, c_ptr.p);
-    SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
-              c_t2.p);
+    if (cnnz > 0)  // (every archetype can be a hub archetype on tiny problems: no sparse candidates at all)
+      SC_LAUNCH(ctx, k_gather_cand, (unsigned)((cnnz + 255) / 256), 256, 0, cnnz, co_out.p, c_cellv.p, c_t2v.p, c_cell.p,
+                c_t2.p);
   }
   if (n_hub > 0) {  // hub block (chosen above): slices of t1 by hub column, running product, per-CTA partial results
     const int nloc = row_end - row_begin;
@@ -2718,11 +2719,13 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
   }
   SC_CUDA(ctx, cudaEventRecord(ev_a[t], ctx->stream));
   if (t == 0 && n_hub > 0) SC_TRY(build_perm());  // the order only affects locality; reused for the remaining steps
-  if (nchunks > 0) {
+  {
     // largest entry of every K B row (second pruning bound): produced by k_kb_merge when it ran, else computed here
-    if (t < 2 || fresh_kb)
+    if (nchunks > 0 && row_end > row_begin && (t < 2 || fresh_kb))
       SC_LAUNCH(ctx, k_row_max, (unsigned)(((size_t)(row_end - row_begin) * 32 + 255) / 256), 256, 0, row_begin, row_end,
                 KB.view(), cmax_v.p, cmax_l.p);
+    // round 0 runs for every archetype on every rank (an archetype without local candidates reports +inf): the
+    // all-gather of the bounds below is a collective, so it cannot depend on what this rank happens to own
     SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
               bound_v.p, bound_v.p);
     if (ctx->world() > 1) {
@@ -2737,8 +2740,9 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
       prune = bound_all.p + (size_t)w * k;
       SC_LAUNCH(ctx, k_min_over_ranks, (k + 255) / 256, 256, 0, k, w, bound_all.p, bound_all.p + (size_t)w * k);
     }
-    SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
-              part_v.p, part_i.p, bound_v.p, prune);
+    if (nchunks > 0)
+      SC_LAUNCH(ctx, k_updateB_eval, (unsigned)nchunks, 256, 0, g, 1, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p,
+                part_v.p, part_i.p, bound_v.p, prune);
   }
   if (n_hub > 0 && !hub_async) SC_TRY(launch_hub(t, ctx->stream, partial_dev));
   SC_CUDA(ctx, cudaEventRecord(ev_b[t], ctx->stream));

@@ -4,11 +4,15 @@
 //   M            CSR int32/int32/fp64                       ~ 24 nnz per row
 //   A slots      a_idx[n*S] int32, a_val[n*S] fp64, a_cnt[n]  (column j of A = slots of cell j)
 //   B slots      b_idx[k*S] int32, b_val[k*S] fp64, b_cnt[k]  (column a of B = slots of archetype a)
-//   KB rows      per-cell lists (archetype, (K B)[cell, archetype]), K = M M^T applied as M (M .)   ~ 40 per cell
+//   K            K = M M^T (cpu.py:128,157) as row lists, first-occurrence order, ~770 entries per row at 1M cells; a rank
+//                of a sharded job keeps the columns of its own cells only
+//   KB rows      per-cell lists (archetype, (K B)[cell, archetype]) sorted by archetype                  ~ 55 per cell
 //   t1A          dense k x k fp64, t1A[i'][i] = (B^T K B)[i, i']      (gradient term of _updateA, cpu.py:442)
 //   t1B          dense k x k fp64, A A^T                                (gradient term of _updateB, cpu.py:480)
-//   C_a          per-archetype candidate lists (cell, (K A^T)[cell, a]) (cpu.py:481), the support of t2
-// Nothing of size n x k or n x n is ever formed.
+//   C_a          per-archetype candidate lists (cell, (K A^T)[cell, a]) (cpu.py:481), the support of t2, for the
+//                ordinary archetypes; T2H / HH: dense [cells x 64] t2 and running product of the hub archetypes
+// Nothing of size n x k or n x n is ever formed.  Multi-GPU: cells are sharded by contiguous slabs, everything a rank
+// needs from the others arrives through sc_fit::exchange (an in-place all-gather of equal slabs, comm.cuh).
 //
 // Exactness of the candidate restriction (SURVEY.md §8a notes): K, A, B >= 0, so a gradient entry can be negative only
 // on the support of t2.  If the minimum over that support is < 0 it is the column argmin; otherwise the column is

@@ -62,8 +62,6 @@ struct sc_fit {
   bool fresh_kb = false;  // SC_FIT_FRESH_KB=1: re-evaluate K B from B at every Frank-Wolfe step instead
   bool resum_A = false;   // SC_FIT_RESUM_A=1: _updateA re-sums (t1 A) over the active slots at every step
   DBuf<long long> b_off;
-  DBuf<unsigned long long> bk_in, bk_out;
-  DBuf<double> bv_in;
   DBuf<double> t1A, t1B;
   // _updateB precompute
   RowListsBuf MA, MAg, T2c;

@@ -1758,7 +1758,7 @@ k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __r
                   double c_new, double* __restrict__ max_v, int* __restrict__ max_l, int* __restrict__ slow_list,
                   int* __restrict__ slow_count) {
   __shared__ double s_dv[KBM_ECAP];
-  __shared__ int s_dk[KBM_ECAP];
+  __shared__ __align__(16) int s_dk[KBM_ECAP];  // every row's keys start at a multiple of 4 and are padded to one (key -3)
   __shared__ unsigned char s_match[KBM_ECAP];
   __shared__ long long s_pd[KBM_ROWS];
   __shared__ int s_ld[KBM_ROWS], s_doff[KBM_ROWS + 1];
@@ -1774,8 +1774,8 @@ k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __r
     s_ld[threadIdx.x] = ld;
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of 64 lengths by one warp
-    const int a = s_ld[lane], b = s_ld[lane + 32];
+  if (warp == 0) {  // exclusive scan of the 64 lengths, each rounded up to a multiple of 4, by one warp
+    const int a = (s_ld[lane] + 3) & ~3, b = (s_ld[lane + 32] + 3) & ~3;
     int ia = a, ib = b;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1794,12 +1794,12 @@ k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __r
   __syncthreads();
   for (int j = 0; j < KBM_ROWS / 8; ++j) {  // stage the delta rows: warp w takes rows w, w + 8, ...
     const int rr = warp + 8 * j;
-    const int ld = s_ld[rr], doff = s_doff[rr];
-    if (doff + ld > KBM_ECAP) continue;
+    const int ld = s_ld[rr], doff = s_doff[rr], ldp = (ld + 3) & ~3;
+    if (doff + ldp > KBM_ECAP) continue;
     const long long pd = s_pd[rr];
-    for (int x = lane; x < ld; x += 32) {
-      s_dk[doff + x] = D.key[pd + x];
-      s_dv[doff + x] = D.val[pd + x];
+    for (int x = lane; x < ldp; x += 32) {
+      s_dk[doff + x] = x < ld ? D.key[pd + x] : -3;
+      s_dv[doff + x] = x < ld ? D.val[pd + x] : 0.0;
     }
   }
   __syncthreads();
@@ -1807,8 +1807,8 @@ k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __r
     const int rr = warp + 8 * j;
     if (rr >= nrow) break;
     const int i = row0 + rr;
-    const int ld = s_ld[rr], doff = s_doff[rr];
-    if (doff + ld > KBM_ECAP) {  // does not fit the staging area: the generic kernel takes this row
+    const int ld = s_ld[rr], doff = s_doff[rr], ldp = (ld + 3) & ~3;
+    if (doff + ldp > KBM_ECAP) {  // does not fit the staging area: the generic kernel takes this row
       if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = i;
       continue;
     }
@@ -1824,10 +1824,17 @@ k_kb_merge_staged(int r0, int r1, RowLists Old, RowLists D, const long long* __r
         ok = Old.key[po + ob + lane];
         val = __dmul_rn(c_old, Old.val[po + ob + lane]);
       }
-      for (int d = 0; d < ld; ++d) {
-        if (ok == s_dk[doff + d]) {
-          val = __dadd_rn(val, __dmul_rn(c_new, s_dv[doff + d]));
-          s_match[doff + d] = 1;
+      // four staged keys per shared-memory load (an old key equals at most one delta key; pad keys never match)
+      for (int d = 0; d < ldp; d += 4) {
+        const int4 kk = *reinterpret_cast<const int4*>(&s_dk[doff + d]);
+        int hit = -1;
+        if (ok == kk.x) hit = d;
+        if (ok == kk.y) hit = d + 1;
+        if (ok == kk.z) hit = d + 2;
+        if (ok == kk.w) hit = d + 3;
+        if (hit >= 0) {
+          val = __dadd_rn(val, __dmul_rn(c_new, s_dv[doff + hit]));
+          s_match[doff + hit] = 1;
         }
       }
       if (ov) {

@@ -168,7 +168,7 @@ def cpu_fit_replicas(n, procs, reps):
     replicas are how it uses every host core); returns per-rep wall seconds (max over the replicas), iterations, k."""
     import multiprocessing as mp
     with mp.get_context("spawn").Pool(procs) as pool:
-        res = pool.map(_cpu_replica, [(n, 0, reps)] * procs)
+        res = pool.map_async(_cpu_replica, [(n, 0, reps)] * procs).get(timeout=1700)  # never hang the arm
     per_rep = [max(r[0][i] for r in res) for i in range(reps)]
     return per_rep, res[0][1], res[0][2]
 

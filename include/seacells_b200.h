@@ -46,9 +46,12 @@ const char* sc_version(void);
  * ranks owns the cells [rank * slab, (rank + 1) * slab), slab = ceil(n / world): sc_kernel_build searches the neighbours
  * of its slab only, sc_fit_update_A fills its columns of A, sc_fit_update_B evaluates its rows of the gradient, and the
  * library exchanges what the other ranks need on its own stream with ONE collective, an in-place all-gather of equal
- * slabs (compressed A, per-cell RSS terms, per-archetype {candidate min G, cell, non-candidate G, cell} argmin partials,
- * kNN rows, candidate counts).  No floating-point value is reduced across ranks, so results are bitwise identical to a
- * single-GPU run.  Every rank must make the same calls in the same order with the same M, archetypes and A0.
+ * slabs (compressed A, per-cell RSS terms, rows of A A^T by archetype slab, rows of M A^T, the K B rows of supp(B), kNN
+ * rows, per step the round-0 pruning bounds and the per-archetype {candidate min G, cell, non-candidate G, cell} argmin
+ * partials).  No floating-point value is reduced across ranks, so results are bitwise identical to a single-GPU run.
+ * Every rank must make the same calls in the same order with the same M, archetypes and A0, and a context must join
+ * its job BEFORE any handle (sc_kernel, sc_fit) is created on it.  A rank's sc_fit forms only the columns of K = M M^T
+ * that belong to its own cells.  The argmin trace of sc_fit_update_A covers the rank's own cells only.
  *   sc_nccl_unique_id + sc_ctx_init_nccl   one process per GPU: rank 0 creates the 128-byte id, the host broadcasts it
  *                                          (torch.distributed, MPI, a file ...), every rank joins; libnccl.so.2 is
  *                                          resolved with dlopen (sc_nccl_load_library gives an explicit path)

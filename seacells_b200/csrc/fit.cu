@@ -2768,7 +2768,7 @@ int sc_fit::update_B_eval(int t, double* partial_dev) {
     // round 0 runs for every archetype on every rank (an archetype without local candidates reports +inf): the
     // all-gather of the bounds below is a collective, so it cannot depend on what this rank happens to own
     SC_LAUNCH(ctx, k_updateB_eval, k, 256, 0, g, 0, chunk_ptr.p, chunk_arch.p, cmax_v.p, cmax_l.p, part_v.p, part_i.p,
-              bound_v.p, bound_v.p);
+              bound_v.p, bound_v.p);  // round 0 prunes against +inf: the last argument is never read
     if (ctx->world() > 1) {
       // every rank evaluated the 64 / world largest-t2 candidates of each archetype among ITS cells; the smallest of the
       // round-0 minima is the bound all of them prune with (one more k x 8-byte all-gather per step, instead of every
